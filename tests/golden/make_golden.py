@@ -1,0 +1,159 @@
+"""Generate golden fixtures from the REFERENCE's own code (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference (read-only)
+
+The reference is Python, so its path-owned functions are imported from where they lie and run
+on CPU; the Perspective-Crop-Layer closure (a nested block inside a dataset `__getitem__`,
+`src/datasets/hands_light_dataset.py:354-467`) is exec'd from the file's own lines at
+generation time -- nothing is copied into this repository.  The resulting .npz files are
+committed; tests never read /root/reference.
+
+`smplx` (the MANO arithmetic) cannot be imported (absent), so no golden exists for it: that
+part of the oracle is "parity unpinned" (see oracle/geometry_oracle.py header).
+"""
+import math
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = os.environ.get("HANDS_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+import common.camera as ref_camera  # noqa: E402
+import common.data_utils as ref_data_utils  # noqa: E402
+import common.rot as ref_rot  # noqa: E402
+import common.transforms as ref_tf  # noqa: E402
+
+from hands_b200.synthetic import random_rotmats, synthetic_head_inputs, synthetic_pcl_inputs  # noqa: E402
+
+
+def golden_logmap():
+    g = torch.Generator().manual_seed(7)
+    R = torch.cat(
+        [
+            random_rotmats(40, g),
+            random_rotmats(8, g, edge="identity"),
+            random_rotmats(16, g, edge="near_pi"),
+        ]
+    )
+    # small rotations around random axes (exercise the small-angle neighbourhood)
+    tiny = ref_rot.quaternion_to_matrix(
+        torch.nn.functional.normalize(
+            torch.cat([torch.ones(8, 1), 1e-4 * torch.randn(8, 3, generator=g)], dim=1), dim=1
+        )
+    )
+    R = torch.cat([R, tiny]).contiguous().requires_grad_(True)
+    aa = ref_rot.matrix_to_axis_angle(R)
+    w = torch.randn(aa.shape, generator=g)
+    (gR,) = torch.autograd.grad((aa * w).sum(), R)
+    quat = ref_rot.matrix_to_quaternion(R.detach())
+    np.savez_compressed(
+        os.path.join(HERE, "logmap.npz"),
+        R=R.detach().numpy(), aa=aa.detach().numpy(), quat=quat.numpy(), w=w.numpy(), gR=gR.numpy(),
+    )
+
+
+def golden_camera_projection():
+    B = 32
+    rotmat, betas, cam, K = synthetic_head_inputs(B, seed=3, small_s_frac=0.25)
+    f = (K[:, 0, 0] + K[:, 1, 1]) / 2
+    cam = cam.clone().requires_grad_(True)
+    cam_t = ref_camera.weak_perspective_to_perspective_torch(cam, focal_length=f, img_res=224, min_s=0.1)
+    g = torch.Generator().manual_seed(11)
+    w3 = torch.randn(B, 3, generator=g)
+    (g_cam,) = torch.autograd.grad((cam_t * w3).sum(), cam)
+    wp = ref_camera.perspective_to_weak_perspective_torch(cam_t.detach(), f, 224)
+    pts = (torch.randn(B, 21, 3, generator=g) * 0.05 + cam_t.detach()[:, None]).requires_grad_(True)
+    j2d = ref_tf.project2d_batch(K, pts)
+    j2d_n = ref_data_utils.normalize_kp2d(j2d, 224)
+    w2 = torch.randn(B, 21, 2, generator=g)
+    (g_pts,) = torch.autograd.grad((j2d_n * w2).sum(), pts)
+    j2d_un = ref_data_utils.unormalize_kp2d(j2d_n.detach(), 224)
+    np.savez_compressed(
+        os.path.join(HERE, "camera_projection.npz"),
+        cam=cam.detach().numpy(), K=K.numpy(), f=f.numpy(), cam_t=cam_t.detach().numpy(), w3=w3.numpy(),
+        g_cam=g_cam.numpy(), wp=wp.numpy(), pts=pts.detach().numpy(), j2d=j2d.detach().numpy(),
+        j2d_norm=j2d_n.detach().numpy(), w2=w2.numpy(), g_pts=g_pts.numpy(), j2d_un=j2d_un.numpy(),
+    )
+
+
+def _pcl_closure_source():
+    """Lines 357-467 of the reference dataset file (the body of `if 'pcl' in args.pos_enc:`)."""
+    path = os.path.join(REF, "src/datasets/hands_light_dataset.py")
+    with open(path) as fh:
+        lines = fh.readlines()
+    assert "if 'pcl' in args.pos_enc" in lines[353], lines[353]
+    return textwrap.dedent("".join(lines[355:467]))
+
+
+def run_reference_pcl(img, r_bbox, l_bbox, intrx, img_res):
+    ns = {
+        "math": math, "np": np, "torch": torch, "F": F,
+        "inputs": {"img": img, "r_bbox": np.asarray(r_bbox), "l_bbox": np.asarray(l_bbox)},
+        "intrx": np.asarray(intrx, dtype=np.float64),
+        "args": types.SimpleNamespace(img_res=img_res, pos_enc="pcl"),
+    }
+    exec(compile(_pcl_closure_source(), "<reference pcl closure>", "exec"), ns)
+    i = ns["inputs"]
+    return i["r_img"], i["l_img"], i["r_rot"], i["l_rot"], ns["r_grid_perspective"], ns["l_grid_perspective"]
+
+
+def golden_pcl():
+    out = {}
+    # (a) small images, full outputs.  img_res=64; bboxes include: generic, square, zero-size (s -> img_res),
+    #     centred on the principal point (R = I), touching the border.
+    res = 64
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.randn(4, 3, res, res, generator=g)
+    Ks = np.array([[[90.0, 0, 32], [0, 90.0, 32], [0, 0, 1]],
+                   [[60.0, 0, 30], [0, 75.0, 34], [0, 0, 1]],
+                   [[150.0, 0, 32], [0, 150.0, 32], [0, 0, 1]],
+                   [[40.0, 0, 32], [0, 40.0, 32], [0, 0, 1]]])
+    r_boxes = np.array([[5, 8, 40, 30], [20, 20, 44, 44], [10, 10, 10, 10], [0, 0, 63, 63]], dtype=np.int16)
+    l_boxes = np.array([[30, 2, 60, 50], [12, 12, 52, 52], [40, 3, 62, 20], [1, 30, 18, 62]], dtype=np.int16)
+    crops, rots, grids_sizes = [], [], []
+    for b in range(4):
+        r_img, l_img, r_rot, l_rot, r_grid, l_grid = run_reference_pcl(imgs[b], r_boxes[b], l_boxes[b], Ks[b], res)
+        crops += [r_img.numpy(), l_img.numpy()]
+        rots += [r_rot.numpy(), l_rot.numpy()]
+        grids_sizes += [r_grid.shape[0], l_grid.shape[0]]
+        out[f"grid_{2*b}"] = r_grid.numpy()
+        out[f"grid_{2*b+1}"] = l_grid.numpy()
+    out["small_img"] = imgs.numpy()
+    out["small_K"] = Ks
+    out["small_bbox"] = np.stack([r_boxes, l_boxes], axis=1).reshape(8, 4)  # row 2b = right, 2b+1 = left
+    out["small_crop"] = np.stack(crops)
+    out["small_rot"] = np.stack(rots)
+    out["small_s"] = np.array(grids_sizes)
+    # (b) full-size 224 case from the synthetic generator (inputs regenerated from the seed in the test);
+    #     outputs stored sub-sampled [::4, ::4] to keep the fixture small.
+    img, bbox, K = synthetic_pcl_inputs(4, seed=9, img_res=224)
+    sub, rots, sizes = [], [], []
+    for b in range(0, 4, 2):
+        r_img, l_img, r_rot, l_rot, r_grid, l_grid = run_reference_pcl(
+            img[b], bbox[b].numpy().astype(np.int16), bbox[b + 1].numpy().astype(np.int16), K[b].numpy(), 224)
+        sub += [r_img.numpy()[:, ::4, ::4], l_img.numpy()[:, ::4, ::4]]
+        rots += [r_rot.numpy(), l_rot.numpy()]
+        sizes += [r_grid.shape[0], l_grid.shape[0]]
+    out["full_seed"] = np.array(9)
+    out["full_crop_sub4"] = np.stack(sub)       # crop j uses image (j//2)*2, bbox j, K (j//2)*2
+    out["full_rot"] = np.stack(rots)
+    out["full_s"] = np.array(sizes)
+    np.savez_compressed(os.path.join(HERE, "pcl.npz"), **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    golden_logmap()
+    golden_camera_projection()
+    golden_pcl()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
