@@ -1,0 +1,79 @@
+"""ctypes binding of libhands_b200.so (the C ABI declared in include/hands_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or a
+call returns non-zero, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+from . import _build
+
+c_float_p = ctypes.c_void_p  # device / host pointers are passed as integers
+_lib = None
+
+SYMBOLS = {
+    "hb_last_error_string": (ctypes.c_char_p, []),
+    "hb_version": (ctypes.c_int, []),
+    "hb_launch_count": (ctypes.c_uint64, []),
+    "hb_mano_create": (ctypes.c_int, [ctypes.c_void_p] * 8 + [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "hb_mano_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "hb_mano_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "hb_mano_head_fwd": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float]
+        + [ctypes.c_void_p] * 6 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
+    ),
+    "hb_mano_head_bwd": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float]
+        + [ctypes.c_void_p] * 6 + [ctypes.c_void_p] * 5 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
+    ),
+    "hb_matrix_to_axis_angle_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_matrix_to_axis_angle_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_project2d_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_project2d_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_weak_to_persp_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_weak_to_persp_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_persp_to_weak_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_rot_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_pcl_setup": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_pcl_homography_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_pcl_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_pcl_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hb_pcl_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+}
+
+PCL_PARAM_FLOATS = 32
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) and type the library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here means the .so does not match include/hands_b200.h
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().hb_last_error_string()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count():
+    return int(load().hb_launch_count())

@@ -1,0 +1,151 @@
+"""Drop-in for the reference's common/body_models.py: `build_mano_aa` and the mesh index constants.
+
+`build_mano_aa(is_rhand, create_transl=False, flat_hand=False)` returns an `nn.Module` whose
+`forward(betas=, global_orient=, hand_pose=, transl=None)` yields `.vertices (B,778,3)` and
+`.joints (B,21,3)` like `smplx.MANO(use_pca=False)` with the fingertip selector enabled
+(SURVEY.md Appendix A), computed by libhands_b200.so.  Buffers are registered under the smplx names
+so reference checkpoints load (`v_template, shapedirs, posedirs, J_regressor, lbs_weights, parents,
+faces_tensor, pose_mean`).
+
+Constants come from `$MANO_DIR/MANO_{RIGHT,LEFT}.pkl` when present (read lazily, not at import --
+body_models.py:90 of the reference reads the env at import and fails without it); otherwise, when
+`HANDS_B200_SYNTHETIC_MANO=1` or `synthetic=True`, from the seeded MANO-shaped generator used by the
+tests and benchmarks (the licensed files cannot be shipped).
+"""
+import os
+import pickle
+from collections import namedtuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..functional import ManoHandle, ManoHeadFunction
+from ..synthetic import TIP_IDS, synthetic_mano_buffers
+
+ManoOutput = namedtuple("ManoOutput", ["vertices", "joints", "betas", "global_orient", "hand_pose", "full_pose"])
+
+# wrist-sealing fan (reference body_models.py:35-58): ring order, extra centre vertex = 778
+_SEAL_RING = (120, 108, 79, 78, 121, 214, 215, 279, 239, 234, 92, 38, 122, 118, 117, 119)
+SEAL_FACES_R = [[_SEAL_RING[i], _SEAL_RING[(i + 1) % 16], 778] for i in range(16)]
+CIRCLE_V_ID = np.array(_SEAL_RING[1:] + _SEAL_RING[:1], dtype=np.int64)
+
+
+def seal_mano_mesh(v3d, faces, is_rhand):
+    """v3d (B,778,3), faces (1538,3) -> (B,779,3), (1554,3)  (reference body_models.py:60-72)."""
+    fan = torch.as_tensor(SEAL_FACES_R, dtype=torch.long, device=faces.device)
+    if not is_rhand:
+        fan = fan[:, [1, 0, 2]]  # flip the winding for the left hand
+    centre = v3d[:, torch.as_tensor(CIRCLE_V_ID, device=v3d.device)].mean(dim=1, keepdim=True)
+    return torch.cat((v3d, centre), dim=1), torch.cat((faces, fan), dim=0)
+
+
+def _to_np(x):
+    """MANO pickles hold chumpy arrays / scipy sparse matrices; reduce to a dense float array."""
+    if hasattr(x, "todense"):
+        x = x.todense()
+    if hasattr(x, "r"):
+        x = x.r
+    return np.asarray(x)
+
+
+def load_mano_pkl(path, flat_hand_mean=False):
+    """Read an official MANO_{RIGHT,LEFT}.pkl into the smplx buffer layout."""
+    with open(path, "rb") as fh:
+        d = pickle.load(fh, encoding="latin1")
+    shapedirs = _to_np(d["shapedirs"])[:, :, :10]
+    posedirs = _to_np(d["posedirs"])
+    hands_mean = np.zeros(45) if flat_hand_mean else _to_np(d["hands_mean"]).reshape(45)
+    parents = _to_np(d["kintree_table"])[0].astype(np.int64).copy()
+    parents[0] = -1
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)  # noqa: E731
+    return {
+        "v_template": t(_to_np(d["v_template"])),
+        "shapedirs": t(shapedirs),
+        "posedirs": t(posedirs.reshape(-1, posedirs.shape[-1]).T),
+        "J_regressor": t(_to_np(d["J_regressor"])),
+        "lbs_weights": t(_to_np(d["weights"])),
+        "parents": torch.as_tensor(parents),
+        "pose_mean": t(np.concatenate([np.zeros(3), hands_mean])),
+        "faces": torch.as_tensor(_to_np(d["f"]).astype(np.int64)),
+        "tip_ids": torch.tensor(TIP_IDS, dtype=torch.int64),
+    }
+
+
+class MANOLayer(nn.Module):
+    """B200-native stand-in for `smplx.MANO(model_path, use_pca=False, is_rhand=..., flat_hand_mean=...)`."""
+
+    NUM_HAND_JOINTS = 15
+
+    def __init__(self, buffers, is_rhand=True, create_transl=False):
+        super().__init__()
+        self.is_rhand = is_rhand
+        for name in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "pose_mean"):
+            self.register_buffer(name, buffers[name].float().clone())
+        self.register_buffer("parents", buffers["parents"].long().clone())
+        self.register_buffer("faces_tensor", buffers["faces"].long().clone())
+        self.register_buffer("tip_ids", buffers["tip_ids"].long().clone())
+        self.faces = buffers["faces"].cpu().numpy()
+        # smplx keeps 1-row default parameters in parameters()/state_dict()
+        self.betas = nn.Parameter(torch.zeros(1, 10))
+        self.global_orient = nn.Parameter(torch.zeros(1, 3))
+        self.hand_pose = nn.Parameter(torch.zeros(1, 45))
+        if create_transl:
+            self.transl = nn.Parameter(torch.zeros(1, 3))
+        self._handles = {}
+
+    def handle(self, device):
+        """hb_mano* for `device` (built on first use; rebuilt if the module moved)."""
+        key = (device.type, device.index)
+        h = self._handles.get(key)
+        if h is None:
+            if device.type != "cuda":
+                raise RuntimeError("hands_b200 MANO layer has no CPU path; move the module and inputs to a CUDA device")
+            bufs = {k: getattr(self, k) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "parents", "pose_mean", "tip_ids")}
+            h = ManoHandle(bufs, device)
+            self._handles[key] = h
+        return h
+
+    def forward(self, betas=None, global_orient=None, hand_pose=None, transl=None, return_verts=True, return_full_pose=False, **kwargs):
+        ref = next(t for t in (betas, global_orient, hand_pose, self.v_template) if t is not None)
+        B = max(t.shape[0] for t in (betas, global_orient, hand_pose) if t is not None) if any(t is not None for t in (betas, global_orient, hand_pose)) else 1
+        betas = self.betas.expand(B, -1) if betas is None else betas
+        global_orient = self.global_orient.expand(B, -1) if global_orient is None else global_orient
+        hand_pose = self.hand_pose.expand(B, -1) if hand_pose is None else hand_pose
+        if transl is None and hasattr(self, "transl"):
+            transl = self.transl.expand(B, -1)
+        if betas.shape[0] != B:
+            betas = betas.expand(B, -1)
+        pose = torch.cat([global_orient.reshape(B, 3), hand_pose.reshape(B, 45)], dim=1)
+        h = self.handle(ref.device if ref.is_cuda else self.v_template.device)
+        verts, _, joints, _, _, _ = ManoHeadFunction.apply(h, pose, betas, None, None, transl, None, 0.0, 0.0)
+        full_pose = pose + self.pose_mean if return_full_pose else None
+        return ManoOutput(verts, joints, betas, global_orient, hand_pose, full_pose)
+
+
+def _buffers_for(is_rhand, flat_hand, synthetic):
+    mano_dir = os.environ.get("MANO_DIR")
+    if not synthetic and mano_dir:
+        for cand in (mano_dir, os.path.join(mano_dir, "mano")):
+            path = os.path.join(cand, "MANO_RIGHT.pkl" if is_rhand else "MANO_LEFT.pkl")
+            if os.path.exists(path):
+                return load_mano_pkl(path, flat_hand_mean=flat_hand)
+    if synthetic or os.environ.get("HANDS_B200_SYNTHETIC_MANO") == "1":
+        return synthetic_mano_buffers(is_rhand, flat_hand=flat_hand)
+    raise FileNotFoundError(
+        "MANO model files not found: set MANO_DIR to the directory holding MANO_RIGHT.pkl/MANO_LEFT.pkl, "
+        "or set HANDS_B200_SYNTHETIC_MANO=1 for seeded MANO-shaped constants (tests/benchmarks)"
+    )
+
+
+def build_mano_aa(is_rhand, create_transl=False, flat_hand=False, synthetic=False):
+    """Same signature as the reference's build_mano_aa (common/body_models.py:92-99)."""
+    return MANOLayer(_buffers_for(is_rhand, flat_hand, synthetic), is_rhand=is_rhand, create_transl=create_transl)
+
+
+def build_layers(device=None, synthetic=False):
+    """Reference build_layers (body_models.py:75-88) minus the ARCTIC object tensors (out of scope)."""
+    layers = {"right": build_mano_aa(True, synthetic=synthetic), "left": build_mano_aa(False, synthetic=synthetic)}
+    if device is not None:
+        layers = {k: v.to(device) for k, v in layers.items()}
+    return layers

@@ -1,0 +1,45 @@
+"""Drop-in for the reference's src/nets/hand_heads/mano_head.py:12-65 (`MANOHead`).
+
+Same constructor, same `forward(rotmat, shape, cam, K)`, same nine `xdict` keys with the `.r`/`.l`
+postfix; the whole chain (log map -> MANO -> weak-persp camera -> cam-space add -> projection ->
+normalisation) is two CUDA launches forward and three backward instead of ~150 torch ops.
+"""
+import torch.nn as nn
+
+from ....common.body_models import build_mano_aa
+from ....common.xdict import xdict
+from ....functional import ManoHeadFunction
+
+
+class MANOHead(nn.Module):
+    def __init__(self, is_rhand, focal_length, img_res, synthetic=False):
+        super().__init__()
+        self.mano = build_mano_aa(is_rhand, synthetic=synthetic)
+        self.focal_length = focal_length
+        self.img_res = img_res
+        self.is_rhand = is_rhand
+
+    def forward(self, rotmat, shape, cam, K, pre_rot=None):
+        """
+        rotmat: (B,16,3,3) rotation matrices, or (B,48) axis-angle
+        shape:  (B,10) betas;  cam: (B,3) weak-perspective [s,tx,ty];  K: (B,3,3) intrinsics
+        pre_rot (extension, default None): (B,3,3) R_virt2orig fused onto the global orientation
+                (the PCL fix-up of hands_light/model.py:330-334) instead of a separate in-place bmm.
+        """
+        rotmat_original = rotmat.clone()
+        pose = rotmat if rotmat.shape[-1] == 48 else rotmat.reshape(-1, 16, 3, 3)
+        handle = self.mano.handle(shape.device)
+        vertices, v3d_cam, joints3d, j3d_cam, j2d_norm, cam_t = ManoHeadFunction.apply(
+            handle, pose, shape, cam, K, None, pre_rot, float(self.img_res), 0.1
+        )
+        output = xdict()
+        output["cam_t.wp"] = cam
+        output["cam_t"] = cam_t
+        output["joints3d"] = joints3d
+        output["vertices"] = vertices
+        output["j3d.cam"] = j3d_cam
+        output["v3d.cam"] = v3d_cam
+        output["j2d.norm"] = j2d_norm
+        output["beta"] = shape
+        output["pose"] = rotmat_original
+        return output.postfix(".r" if self.is_rhand else ".l")

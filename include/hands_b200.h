@@ -1,0 +1,144 @@
+/*
+ * hands_b200.h -- C ABI of libhands_b200.so: the geometry hot path of ap229997/hands
+ * (MANO layer + LBS + camera/projection + Perspective Crop Layer), forward and backward,
+ * as hand-written CUDA for sm_100a.
+ *
+ * The reference has no FFI of its own: its seam is a set of Python call signatures
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference code it replaces.
+ * Python (hands_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, <0 = argument error (HB_E_*), >0 = cudaError_t.
+ *     hb_last_error_string() gives the text of the last failure on the calling thread.
+ *   - all tensors are fp32, contiguous, row-major; pointers are DEVICE pointers unless the
+ *     parameter name ends in _host.  Float buffers must be 8-byte aligned.
+ *   - the caller allocates and owns every buffer, including the workspace; the library never
+ *     allocates per call and never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.
+ *   - nullable pointers are marked "or NULL"; a NULL output is simply not written, a NULL
+ *     upstream gradient counts as zero.
+ */
+#ifndef HANDS_B200_H
+#define HANDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define HB_E_ARG (-1)      /* NULL / negative size / bad flag            */
+#define HB_E_ALIGN (-2)    /* a float buffer is not 8-byte aligned       */
+#define HB_E_WORKSPACE (-3)/* workspace too small                        */
+#define HB_E_UNSUPPORTED (-4)
+
+#define HB_NUM_VERTS 778
+#define HB_NUM_JOINTS 16
+#define HB_NUM_OUT_JOINTS 21
+#define HB_NUM_BETAS 10
+
+typedef struct hb_mano hb_mano; /* opaque: MANO constants of one hand side on one device */
+
+const char* hb_last_error_string(void);
+int hb_version(void);
+
+/* ---- MANO constants --------------------------------------------------------------------
+ * Replaces: common/body_models.py:92-99 build_mano_aa -> smplx.MANO(...) buffer registration.
+ * All inputs are HOST pointers in the smplx buffer layouts:
+ *   v_template (778,3)  shapedirs (778,3,10)  posedirs (135,2334) [column 3v+k]
+ *   J_regressor (16,778)  lbs_weights (778,16)  parents (16)  pose_mean (48)  tip_ids (5)
+ * Copies them to `device` once, re-laid-out for the kernels (joint regression folded into
+ * J_template/J_shapedirs in fp64). */
+int hb_mano_create(const float* v_template_host, const float* shapedirs_host, const float* posedirs_host,
+                   const float* J_regressor_host, const float* lbs_weights_host, const int32_t* parents_host,
+                   const float* pose_mean_host, const int32_t* tip_ids_host, int device, hb_mano** out);
+int hb_mano_destroy(hb_mano* h);
+
+/* Bytes of scratch the fwd / bwd calls need for a batch of B hands. */
+size_t hb_mano_workspace_bytes(int B, int backward);
+
+/* ---- MANO layer + head, forward ----------------------------------------------------------
+ * Replaces: src/nets/hand_heads/mano_head.py:21-65 MANOHead.forward (pose_is_rotmat=1, cam and K
+ * given) and smplx.MANO.forward as called at mano_head.py:34-38, process_arctic.py:16-34,
+ * src/arctic/processing.py:175-188 (pose_is_rotmat=0, cam=K=NULL, optional transl).
+ *   pose      (B,16,3,3) rotation matrices if pose_is_rotmat, else (B,48) axis-angle
+ *   pre_rot   (B,3,3) or NULL: left-multiplied onto joint 0 before the log map
+ *             (src/models/hands_light/model.py:330-334, the PCL orientation fix-up)
+ *   betas (B,10)   cam (B,3)=[s,tx,ty] or NULL   K (B,3,3) or NULL   transl (B,3) or NULL
+ * Outputs (each or NULL): vertices (B,778,3), v3d_cam (B,778,3), joints3d (B,21,3),
+ *   j3d_cam (B,21,3), j2d_norm (B,21,2), cam_t (B,3).  Camera outputs need cam and K. */
+int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot,
+                     const float* betas, const float* cam, const float* K, const float* transl, int B,
+                     float img_res, float min_s, float* vertices, float* v3d_cam, float* joints3d,
+                     float* j3d_cam, float* j2d_norm, float* cam_t, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- backward ----------------------------------------------------------------------------
+ * Same inputs (saved by the caller; everything else is recomputed), upstream gradients of the
+ * six outputs (each or NULL), and gradients w.r.t. pose (same shape as pose), betas, cam
+ * (or NULL), transl (or NULL), pre_rot (or NULL).  K gets no gradient (data in the reference). */
+int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot,
+                     const float* betas, const float* cam, const float* K, const float* transl, int B,
+                     float img_res, float min_s, const float* g_vertices, const float* g_v3d_cam,
+                     const float* g_joints3d, const float* g_j3d_cam, const float* g_j2d_norm,
+                     const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam, float* g_transl,
+                     float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- free functions of the path ------------------------------------------------------------
+ * common/rot.py:180-193 matrix_to_axis_angle, forward and backward; N matrices. */
+int hb_matrix_to_axis_angle_fwd(const float* R, int N, float* aa, void* stream);
+int hb_matrix_to_axis_angle_bwd(const float* R, const float* g_aa, int N, float* g_R, void* stream);
+/* common/transforms.py:316-329 project2d_batch (+ optional data_utils.py:361-365 normalize_kp2d when
+ * img_res > 0): K (B,3,3), pts (B,N,3) -> out (B,N,2); backward w.r.t. pts. */
+int hb_project2d_fwd(const float* K, const float* pts, int B, int N, float img_res, float* out, void* stream);
+int hb_project2d_bwd(const float* K, const float* pts, const float* g_out, int B, int N, float img_res,
+                     float* g_pts, void* stream);
+/* common/camera.py:456-474 weak_perspective_to_perspective_torch and :10-29 its inverse.
+ * focal (B,).  backward of the first w.r.t. cam. */
+int hb_weak_to_persp_fwd(const float* cam, const float* focal, int B, float img_res, float min_s, float* cam_t,
+                         void* stream);
+int hb_weak_to_persp_bwd(const float* cam, const float* focal, const float* g_cam_t, int B, float img_res,
+                         float min_s, float* g_cam, void* stream);
+int hb_persp_to_weak_fwd(const float* cam_t, const float* focal, int B, float img_res, float* cam_wp, void* stream);
+/* src/models/hands_light/model.py:330-334: out[b] = (transpose_R ? R[b]^T : R[b]) @ M[b]; N 3x3 pairs. */
+int hb_rot_apply(const float* R, const float* M, int N, int transpose_R, float* out, void* stream);
+
+/* ---- Perspective Crop Layer ------------------------------------------------------------------
+ * Replaces: src/datasets/hands_light_dataset.py:354-467 (per-sample CPU closure in the data loader).
+ * n_crops crops; crop c samples image c / crops_per_img of `img` (n_crops/crops_per_img, C, R, R).
+ *   bbox (n_crops,4) int32 [x0,y0,x1,y1]; K (n_crops,3,3) fp32.
+ * Step 1 (lines 357-386, 425-454): homography in float64 on the device -> params (n_crops records of
+ *   HB_PCL_PARAM_FLOATS floats, caller-allocated) and R_virt2orig (n_crops,3,3) or NULL. */
+#define HB_PCL_PARAM_FLOATS 32
+int hb_pcl_setup(const int32_t* bbox, const float* K, int n_crops, int img_res, float* params,
+                 float* R_virt2orig, void* stream);
+/* Same arithmetic on the host (float64), one crop: P (9), R (9), s. */
+int hb_pcl_homography_host(const int32_t* bbox_host, const float* K_host, int img_res, float* P_host,
+                           float* R_host, int32_t* s_host);
+/* Step 2 (lines 388-423, 457-462): grid_sample(bilinear, zeros, align_corners=False) to s x s then
+ *   interpolate(bilinear, align_corners=True) to R x R, fused. out (n_crops, C, R, R). */
+int hb_pcl_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int C, int img_res,
+               float* out, void* stream);
+/* Backward w.r.t. img (the grid is data).  g_out (n_crops,C,R,R) -> g_img (n_crops/crops_per_img,C,R,R),
+ *   written exactly once (no atomics, deterministic).  workspace: hb_pcl_bwd_workspace_bytes(). */
+size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int C, int img_res);
+int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res,
+               float* g_img, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- counters ---------------------------------------------------------------------------------
+ * Number of kernels this library has launched since load (all threads). bench.py reports the delta. */
+uint64_t hb_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANDS_B200_H */
