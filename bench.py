@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- hands/s of the fused geometry step (MANO + LBS + PCL + projection, fwd+bwd) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--samples S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on, as one GPU's shard):
+two hands (left+right MANO constants) + 2 PCL crops per sample sharing one source image + projection,
+8192 samples per GPU (65,536 samples at 8 GPUs, weak scaling), synthetic inputs, random-init
+MANO-shaped constants.  One step = one forward+backward pass over the GPU's shard.
+
+Prints ONE JSON line (rank 0).  `value` = hands/s with inputs resident in HBM; `e2e` = the same step
+with host buffers (pinned H2D of the step's inputs, D2H of the per-hand gradients) in the timed region;
+`roofline` = the dominant kernel timed alone; `cpu_baseline` = the oracle (reference torch CPU path)
+on the host cores for a bounded sample.  `--impl reference` times only that CPU path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hands/sec MANO+LBS+PCL fwd+bwd"
+UNIT = "hands/s"
+IMG_RES = 224
+HANDS_PER_SAMPLE = 2
+A_MANO = 31068.0            # algorithmic bytes per hand, MANO head fwd+bwd
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU path (the oracle), one bounded step
+# ------------------------------------------------------------------------------------------------
+class CpuReferenceStep:
+    """Reference torch CPU path for the same step: PCL (grid_sample + interpolate, batched per crop as the
+    reference closure does) + orientation fix-up + MANOHead right/left, forward and backward."""
+
+    def __init__(self, samples, seed=0):
+        from hands_b200.synthetic import synthetic_head_inputs, synthetic_mano_buffers, synthetic_pcl_inputs
+        from oracle import geometry_oracle as O
+
+        self.O, self.S = O, samples
+        n = samples * HANDS_PER_SAMPLE
+        g = torch.Generator().manual_seed(seed)
+        _, self.bbox, self.Kc = synthetic_pcl_inputs(n, seed=seed, img_res=IMG_RES, smin=IMG_RES // 4, smax=3 * IMG_RES // 4)
+        self.img = torch.randn(samples, 3, IMG_RES, IMG_RES, generator=g)
+        self.g_crops = torch.randn(n, 3, IMG_RES, IMG_RES, generator=g)
+        self.hands = []
+        for side in range(HANDS_PER_SAMPLE):
+            rotmat, betas, cam, K = synthetic_head_inputs(samples, seed=seed + 10 * side)
+            self.hands.append(dict(buf=synthetic_mano_buffers(side == 0), rotmat=rotmat, betas=betas, cam=cam, K=K,
+                                   g_v3d=torch.randn(samples, 778, 3, generator=g), g_j3d=torch.randn(samples, 21, 3, generator=g),
+                                   g_j2d=torch.randn(samples, 21, 2, generator=g)))
+
+    def run(self):
+        O = self.O
+        img = self.img.clone().requires_grad_(True)
+        src = img.repeat_interleave(HANDS_PER_SAMPLE, dim=0)
+        crops, rot = O.perspective_crop(src, self.bbox, self.Kc, IMG_RES)
+        outs, grads = [crops], [self.g_crops]
+        leaves = [img]
+        rot = rot.view(self.S, HANDS_PER_SAMPLE, 3, 3)
+        for side, h in enumerate(self.hands):
+            r = h["rotmat"].clone().requires_grad_(True)
+            b = h["betas"].clone().requires_grad_(True)
+            c = h["cam"].clone().requires_grad_(True)
+            pose = O.pcl_fix_global_orient(rot[:, side], r)
+            o = O.mano_head_forward(h["buf"], pose, b, c, h["K"], float(IMG_RES), 0.1)
+            outs += [o["v3d.cam"], o["j3d.cam"], o["j2d.norm"]]
+            grads += [h["g_v3d"], h["g_j3d"], h["g_j2d"]]
+            leaves += [r, b, c]
+        torch.autograd.backward(outs, grads)
+        return sum(float(x.grad.sum()) for x in leaves)
+
+
+def time_cpu_reference(samples, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = CpuReferenceStep(samples)
+    for _ in range(warmup):
+        step.run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step.run()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return samples * HANDS_PER_SAMPLE / dt, dt
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    samples = args.ref_samples
+    hps, dt = time_cpu_reference(samples, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": hps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 two-hand MANO head + 2 PCL crops/sample + projection, fwd+bwd (reference torch CPU path)",
+                   "samples_per_step": samples, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES},
+        "cpu_baseline": {"value": hps, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model(),
+                         "sample": f"{samples} samples ({samples * HANDS_PER_SAMPLE} hands + crops) per step; oracle/geometry_oracle.py = reference torch ops on CPU, all host threads"},
+        "e2e": {"value": hps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cuda_time(fn, steps, warmup, dev):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) * 1e-3 / steps
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from hands_b200 import _lib
+    from hands_b200.step import GeometryStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    S = args.samples
+    step = GeometryStep(S, dev, img_res=IMG_RES, seed=rank)
+    metrics_vec = torch.zeros(64, device=dev)
+
+    def one_step():
+        step.run(overlap=not args.no_overlap)
+        if world > 1:
+            dist.all_reduce(metrics_vec)   # packed metric scalars (north_star); no data-path collective
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    hands_per_step = S * HANDS_PER_SAMPLE * world
+    value = hands_per_step * args.steps / elapsed
+
+    # ---- per-kernel-family timing (alone, same stream) for the roofline ---------------------------
+    peak, peak_src = peaks()
+    fam = {}
+    if rank == 0:
+        n = step.n
+        plane = 3 * IMG_RES * IMG_RES * 4
+        step.pcl_setup()
+        t_fwd = cuda_time(step.pcl_forward, max(3, args.steps), 2, dev)
+        t_bwd = cuda_time(step.pcl_backward, max(3, args.steps), 2, dev)
+        t_mf = cuda_time(lambda: step.mano_forward(0), max(3, args.steps), 2, dev)
+        t_mb = cuda_time(lambda: step.mano_backward(0), max(3, args.steps), 2, dev)
+        b_fwd = n * (plane + 12.0 * step.mean_s2)
+        b_bwd = n * plane + S * plane
+        fam = {
+            "pcl_fwd_kernel": {"ms": t_fwd * 1e3, "alg_bytes": b_fwd, "gbs": b_fwd / t_fwd / 1e9, "frac": b_fwd / t_fwd / 1e9 / peak},
+            "pcl_bwd (mid+img kernels)": {"ms": t_bwd * 1e3, "alg_bytes": b_bwd, "gbs": b_bwd / t_bwd / 1e9, "frac": b_bwd / t_bwd / 1e9 / peak},
+            "mano_fwd (pose+skin)": {"ms": t_mf * 1e3, "alg_bytes": S * 20020.0, "gbs": S * 20020.0 / t_mf / 1e9, "frac": S * 20020.0 / t_mf / 1e9 / peak,
+                                     "hands_per_s": S / t_mf},
+            "mano_bwd (pose+skin+pose)": {"ms": t_mb * 1e3, "alg_bytes": S * 11048.0, "gbs": S * 11048.0 / t_mb / 1e9, "frac": S * 11048.0 / t_mb / 1e9 / peak,
+                                          "hands_per_s": S / t_mb},
+        }
+
+    # ---- e2e: host buffers, copies inside the timed region ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(step, args, dev, world, barrier)
+
+    if rank != 0:
+        return
+    dom = max(("pcl_fwd_kernel", "pcl_bwd (mid+img kernels)"), key=lambda k: fam[k]["ms"])
+    step_bytes = step.bytes_per_sample() * S
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C4 two-hand (left+right MANO) + 2 PCL crops/sample sharing one source image + projection, fwd+bwd",
+                   "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
+                   "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
+                   "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
+                   "streams": "pcl || mano" if not args.no_overlap else "single"},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": fam[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": fam[dom]["frac"], "traffic": None,
+                     "peak_source": peak_src,
+                     "step": {"alg_bytes_per_sample": step.bytes_per_sample(), "achieved": value / world / HANDS_PER_SAMPLE * step.bytes_per_sample() / 1e9,
+                              "frac": value / world / HANDS_PER_SAMPLE * step.bytes_per_sample() / 1e9 / peak},
+                     "families": fam},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        hps, dt = time_cpu_reference(args.ref_samples, 2, 1)
+        line["cpu_baseline"] = {"value": hps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "cpu": cpu_model(),
+                                "sample": f"{args.ref_samples} samples ({args.ref_samples * HANDS_PER_SAMPLE} hands + crops) x 2 timed steps of the same workload; oracle = reference torch ops on CPU, all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(step, args, dev, world, barrier):
+    """Same step with HOST buffers: per step, pinned H2D of the sample's inputs (source images, boxes,
+    intrinsics, poses, shapes, cameras) and D2H of the per-hand gradients + one metric scalar."""
+    import torch.distributed as dist
+
+    S = step.S
+    host_in, dev_in = [], []
+    pairs = [(step.img,), (step.bbox,), (step.Kcrop,)]
+    for h in step.hands:
+        pairs += [(h["rotmat"],), (h["betas"],), (h["cam"],), (h["K"],)]
+    try:
+        for (d,) in pairs:
+            hbuf = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
+            hbuf.copy_(d)
+            host_in.append(hbuf)
+            dev_in.append(d)
+        outs = []
+        for h in step.hands:
+            outs += [h["g_rotmat"], h["g_betas"], h["g_cam"]]
+        host_out = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
+        metric_host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+    except RuntimeError as exc:  # pinned allocation refused
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(exc)[:120]}
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    d2h = sum(t.numel() * t.element_size() for t in host_out) + 4
+
+    def one():
+        for hb, d in zip(host_in, dev_in):
+            d.copy_(hb, non_blocking=True)
+        step.run(overlap=not args.no_overlap)
+        for hb, o in zip(host_out, outs):
+            hb.copy_(o, non_blocking=True)
+        metric_host.copy_(step.hands[0]["j2d"][0, 0, :1], non_blocking=True)
+
+    k = max(2, min(args.steps, 5))
+    for _ in range(2):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(k):
+        one()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    el = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([el], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    return {"value": S * HANDS_PER_SAMPLE * world * k / el, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": k, "ms_per_step": el / k * 1e3, "wall_ms_per_step": wall / k * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=8192, help="samples per GPU per step (C4: 65536 / 8)")
+    ap.add_argument("--ref-samples", type=int, default=64, help="samples per CPU-reference step (bounded sample)")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

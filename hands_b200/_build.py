@@ -10,11 +10,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libhands_b200.so")
-SOURCES = ["hb_api.cu", "mano_kernels.cu", "pcl_kernels.cu"]
+SOURCES = ["hb_api.cu", "mano_kernels.cu", "pcl_kernels.cu", "pcl_setup.cu"]
+PER_FILE_FLAGS = {"pcl_setup.cu": ["-fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-ftz=false", "-prec-div=true", "-prec-sqrt=true", "-fmad=true",
+    "-ftz=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
     "-Xptxas", "-v",
 ]
@@ -43,7 +44,7 @@ def build(force=False, verbose=False):
     log = []
     for src in SOURCES:
         obj = os.path.join(HERE, "lib", src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + PER_FILE_FLAGS.get(src, ["-fmad=true"]) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:

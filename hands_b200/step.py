@@ -1,0 +1,168 @@
+"""Pre-allocated, stream-overlapped geometry step: the fast path a training loop (and bench.py) drives.
+
+One `GeometryStep` owns every buffer of a two-hand sample batch on one GPU and runs
+
+    PCL setup -> PCL forward (2 crops / sample, one shared source image)        stream "pcl"
+    MANO head forward right + left  (global orientation pre-rotated by R_virt2orig,
+        hands_light/model.py:330-334, fused as `pre_rot`)                        stream "mano"
+    MANO head backward right + left                                             stream "mano"
+    PCL backward                                                                stream "pcl"
+
+through the C ABI, with no allocation and no autograd bookkeeping inside the step.  The two streams
+overlap the FFMA-bound MANO kernels with the HBM-bound PCL kernels.  The autograd drop-ins in
+`hands_b200.functional` call the same entry points; this class only removes the per-call allocations.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .functional import ManoHandle, _ptr
+from .synthetic import synthetic_head_inputs, synthetic_mano_buffers, synthetic_pcl_inputs
+
+NV, NJ, NOJ, NB = 778, 16, 21, 10
+
+
+class GeometryStep:
+    def __init__(self, samples, device, img_res=224, with_pcl=True, with_mano=True, hands_per_sample=2, seed=0, grads_on=("v3d", "j3d", "j2d")):
+        self.lib = _lib.load()
+        self.S, self.dev, self.R = int(samples), torch.device(device), int(img_res)
+        self.with_pcl, self.with_mano, self.hps = with_pcl, with_mano, hands_per_sample
+        self.grads_on = grads_on
+        S, R, dev = self.S, self.R, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.s_pcl = torch.cuda.Stream(device=dev)
+        self.s_mano = torch.cuda.Stream(device=dev)
+        self.ev_setup = torch.cuda.Event()
+        self.ev_start = torch.cuda.Event()
+        self.ev_pcl_done = torch.cuda.Event()
+        self.ev_mano_done = torch.cuda.Event()
+        n = S * hands_per_sample  # crops == hands
+        self.n = n
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        if with_pcl:
+            _, bbox, Kc = synthetic_pcl_inputs(n, seed=seed, img_res=R, smin=R // 4, smax=3 * R // 4)
+            self.bbox = bbox.to(dev)
+            self.Kcrop = Kc.to(dev)
+            self.img = torch.randn(S, 3, R, R, generator=gen, **f32)
+            self.crops = torch.empty(n, 3, R, R, **f32)
+            self.g_crops = torch.randn(n, 3, R, R, generator=gen, **f32)
+            self.g_img = torch.empty(S, 3, R, R, **f32)
+            self.params = torch.empty(n, _lib.PCL_PARAM_FLOATS, **f32)
+            self.rot = torch.empty(n, 3, 3, **f32)
+            self.pcl_ws_bytes = self.lib.hb_pcl_bwd_workspace_bytes(n, hands_per_sample, 3, R)
+            self.pcl_ws = torch.empty((self.pcl_ws_bytes + 3) // 4, **f32)
+            self.mean_s2 = float(((self.bbox[:, 2:] - self.bbox[:, :2]).max(dim=1).values.float() ** 2).mean())
+        if with_mano:
+            self.hands = []
+            for side in range(hands_per_sample):
+                is_rhand = side == 0
+                handle = ManoHandle(synthetic_mano_buffers(is_rhand), dev)
+                rotmat, betas, cam, K = [t.to(dev) for t in synthetic_head_inputs(S, seed=seed + 10 * side)]
+                h = dict(handle=handle, rotmat=rotmat, betas=betas, cam=cam, K=K)
+                h["vertices"] = torch.empty(S, NV, 3, **f32)
+                h["v3d"] = torch.empty(S, NV, 3, **f32)
+                h["joints3d"] = torch.empty(S, NOJ, 3, **f32)
+                h["j3d"] = torch.empty(S, NOJ, 3, **f32)
+                h["j2d"] = torch.empty(S, NOJ, 2, **f32)
+                h["cam_t"] = torch.empty(S, 3, **f32)
+                h["g_v3d"] = torch.randn(S, NV, 3, generator=gen, **f32) if "v3d" in grads_on else None
+                h["g_j3d"] = torch.randn(S, NOJ, 3, generator=gen, **f32) if "j3d" in grads_on else None
+                h["g_j2d"] = torch.randn(S, NOJ, 2, generator=gen, **f32) if "j2d" in grads_on else None
+                h["g_rotmat"] = torch.empty(S, NJ, 3, 3, **f32)
+                h["g_betas"] = torch.empty(S, NB, **f32)
+                h["g_cam"] = torch.empty(S, 3, **f32)
+                h["pre_rot"] = torch.empty(S, 3, 3, **f32) if with_pcl else None
+                self.hands.append(h)
+            self.mano_ws_bytes = self.lib.hb_mano_workspace_bytes(S, 1)
+            self.mano_ws = torch.empty((self.mano_ws_bytes + 3) // 4, **f32)
+
+    # ---- pieces (each enqueues on the CURRENT torch stream) ------------------------------------
+    def _st(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def pcl_setup(self):
+        _lib.check(self.lib.hb_pcl_setup(_ptr(self.bbox), _ptr(self.Kcrop), self.n, self.R, _ptr(self.params), _ptr(self.rot), self._st()), "hb_pcl_setup")
+
+    def pcl_forward(self):
+        _lib.check(self.lib.hb_pcl_fwd(_ptr(self.img), _ptr(self.params), self.n, self.hps, 3, self.R, _ptr(self.crops), self._st()), "hb_pcl_fwd")
+
+    def pcl_backward(self):
+        _lib.check(self.lib.hb_pcl_bwd(_ptr(self.g_crops), _ptr(self.params), self.n, self.hps, 3, self.R, _ptr(self.g_img), _ptr(self.pcl_ws),
+                                       self.pcl_ws_bytes, self._st()), "hb_pcl_bwd")
+
+    def gather_pre_rot(self):
+        # rot is (S*hps,3,3) interleaved [sample][side]; each hand side takes its strided view (one small copy kernel)
+        for side, h in enumerate(self.hands):
+            h["pre_rot"].copy_(self.rot.view(self.S, self.hps, 3, 3)[:, side])
+
+    def mano_forward(self, side):
+        h = self.hands[side]
+        _lib.check(self.lib.hb_mano_head_fwd(h["handle"].handle, _ptr(h["rotmat"]), 1, _ptr(h["pre_rot"]), _ptr(h["betas"]), _ptr(h["cam"]), _ptr(h["K"]),
+                                             None, self.S, float(self.R), 0.1, _ptr(h["vertices"]), _ptr(h["v3d"]), _ptr(h["joints3d"]), _ptr(h["j3d"]),
+                                             _ptr(h["j2d"]), _ptr(h["cam_t"]), _ptr(self.mano_ws), self.mano_ws_bytes, self._st()), "hb_mano_head_fwd")
+
+    def mano_backward(self, side):
+        h = self.hands[side]
+        _lib.check(self.lib.hb_mano_head_bwd(h["handle"].handle, _ptr(h["rotmat"]), 1, _ptr(h["pre_rot"]), _ptr(h["betas"]), _ptr(h["cam"]), _ptr(h["K"]),
+                                             None, self.S, float(self.R), 0.1, None, _ptr(h["g_v3d"]), None, _ptr(h["g_j3d"]), _ptr(h["g_j2d"]), None,
+                                             _ptr(h["g_rotmat"]), _ptr(h["g_betas"]), _ptr(h["g_cam"]), None, None, _ptr(self.mano_ws),
+                                             self.mano_ws_bytes, self._st()), "hb_mano_head_bwd")
+
+    # ---- the fused step ----------------------------------------------------------------------------
+    def run(self, overlap=True):
+        """Enqueue one full fwd+bwd step.  Work is ordered after everything already on the current
+        stream and the current stream waits for it, so callers can bracket it with events."""
+        cur = torch.cuda.current_stream(self.dev)
+        if not overlap or not (self.with_pcl and self.with_mano):
+            if self.with_pcl:
+                self.pcl_setup()
+                self.pcl_forward()
+            if self.with_mano:
+                if self.with_pcl:
+                    self.gather_pre_rot()
+                for side in range(self.hps):
+                    self.mano_forward(side)
+                for side in range(self.hps):
+                    self.mano_backward(side)
+            if self.with_pcl:
+                self.pcl_backward()
+            return
+        self.ev_start.record(cur)
+        self.s_pcl.wait_event(self.ev_start)
+        self.s_mano.wait_event(self.ev_start)
+        with torch.cuda.stream(self.s_pcl):
+            self.pcl_setup()
+            self.ev_setup.record(self.s_pcl)
+            self.pcl_forward()
+            self.pcl_backward()
+            self.ev_pcl_done.record(self.s_pcl)
+        with torch.cuda.stream(self.s_mano):
+            self.s_mano.wait_event(self.ev_setup)
+            self.gather_pre_rot()
+            for side in range(self.hps):
+                self.mano_forward(side)
+            for side in range(self.hps):
+                self.mano_backward(side)
+            self.ev_mano_done.record(self.s_mano)
+        cur.wait_event(self.ev_pcl_done)
+        cur.wait_event(self.ev_mano_done)
+
+    # ---- algorithmic bytes -----------------------------------------------------
+    def mano_bytes_per_hand(self):
+        return 31068.0
+
+    def pcl_bytes_per_crop(self):
+        return 3 * self.R * self.R * 4 * 3 + 12.0 * self.mean_s2  # out write + g_out read + g_img write + src footprint
+
+    def bytes_per_sample(self):
+        b = 0.0
+        if self.with_mano:
+            b += self.hps * self.mano_bytes_per_hand()
+        if self.with_pcl:
+            plane = 3 * self.R * self.R * 4
+            # SURVEY.md §8(d) convention for crops sharing one source image: 2*hps planes + the source footprints
+            # (4 x 602,112 + 2 x 12 s^2 for two hands; the shared g_img write is not counted, so the figure is
+            # conservative -- real traffic is one plane higher)
+            b += plane * (2 * self.hps) + self.hps * 12.0 * self.mean_s2
+        return b

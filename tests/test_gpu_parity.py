@@ -258,11 +258,14 @@ def test_pcl_forward_backward_against_oracle(dev, B, cpi, res, smooth):
         (ref_g,) = torch.autograd.grad((ref_crop * w).sum(), xr)
     finally:
         torch.set_num_threads(nt)
-    assert torch.equal(rot.cpu(), ref_rot)
-    assert (crop.detach().cpu() - ref_crop.detach()).abs().max() <= 1e-6
+    # R and P come from a float64 closed-form 3x3 inverse here and from LAPACK in numpy/torch: they can
+    # differ in the last fp32 bit, which moves sample positions by ~1e-5 px.  On white-noise images that is
+    # up to ~2e-5 in the crop; smooth images stay at 1e-6.
+    assert (rot.cpu() - ref_rot).abs().max() <= 1.2e-7
+    err = (crop.detach().cpu() - ref_crop.detach()).abs()
+    assert err.max() <= (2e-6 if smooth else 5e-5), float(err.max())
+    assert float((err <= 1e-6).float().mean()) > 0.99
     assert rel(g_img, ref_g) <= 1e-4
-    if B >= 3:
-        assert torch.allclose(rot[2 * cpi if cpi == 1 else 2].cpu(), torch.eye(3), atol=1e-6) or True
 
 
 def test_no_cpu_fallback():
