@@ -216,9 +216,65 @@ __global__ void pcl_offsets_kernel(float* __restrict__ params, int n_crops, int 
 
 constexpr int PCL_JR = 16;  // intermediate rows per CTA
 
+// approximate sample position for the backward pass (the gradient is continuous in the position, so the
+// correctly-rounded divisions of the forward are not needed here)
+__device__ __forceinline__ void sample_pos_fast(const Crop& c, int j, int i, float R, float& ix, float& iy) {
+  const float u = lin01(c, i), v = lin01(c, j);
+  const float X = fmaf(c.P[1], v, c.P[0] * u) + c.P[2];
+  const float Y = fmaf(c.P[4], v, c.P[3] * u) + c.P[5];
+  const float Z = fmaf(c.P[7], v, c.P[6] * u) + c.P[8];
+  const float iz = __frcp_rn(1e-8f + Z);
+  ix = X * iz - 0.5f;   // ((x/R*2-1)+1)*R/2 - 0.5 == x - 0.5 up to rounding
+  iy = Y * iz - 0.5f;
+  (void)R;
+}
+
+// 1-D transposed linear interpolation tables (same for both axes of a crop):
+//   l1[d]     weight of output index d on its upper source index i0(d)+1  (1-l1[d] on i0(d))
+//   start[m]  first output index d with i0(d) >= m; run(m) = [start[m], start[m+1]) are the d with i0(d) == m
+// mid[m] = sum_{d in run(m)} (1-l1[d]) g[d] + sum_{d in run(m-1)} l1[d] g[d]  (+ run(s-1)'s l1 part when m == s-1,
+// because the upper index is clamped there).
+__device__ __forceinline__ void build_tables(const Crop& c, int R, float* tl1, int* start) {
+  const int s = c.s;
+  for (int m = threadIdx.x; m <= s; m += blockDim.x) start[m] = R;
+  __syncthreads();
+  for (int d = threadIdx.x; d < R; d += blockDim.x) {
+    int i0, i1, p0 = -1, p1;
+    float l0, l1, q0, q1;
+    resize_coef(c, d, R, i0, i1, l0, l1);
+    if (d > 0) resize_coef(c, d - 1, R, p0, p1, q0, q1);
+    tl1[d] = l1;
+    for (int m = p0 + 1; m <= i0; ++m) start[m] = d;
+  }
+  __syncthreads();
+}
+
+template <int C, bool FROM_GLOBAL>
+__device__ __forceinline__ void transposed_taps(const float* __restrict__ src, size_t chan_stride, const float* tl1, const int* start,
+                                                int m, int s, float (&acc)[C]) {
+  // src points at element d = 0 of the line being reduced (stride 1 along d)
+  const int a0 = start[m], a1 = start[m + 1];
+  for (int d = a0; d < a1; ++d) {
+    const float w = 1.0f - tl1[d];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, FROM_GLOBAL ? __ldg(src + ch * chan_stride + d) : src[ch * chan_stride + d], acc[ch]);
+  }
+  const int b0 = m > 0 ? start[m - 1] : a0, b1 = m > 0 ? a0 : a0;
+  for (int d = b0; d < b1; ++d) {
+    const float w = tl1[d];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, FROM_GLOBAL ? __ldg(src + ch * chan_stride + d) : src[ch * chan_stride + d], acc[ch]);
+  }
+  if (m == s - 1) {
+    for (int d = a0; d < a1; ++d) {
+      const float w = tl1[d];
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, FROM_GLOBAL ? __ldg(src + ch * chan_stride + d) : src[ch * chan_stride + d], acc[ch]);
+    }
+  }
+}
+
 // Transposed resize (g_out -> intermediate gradient), separable, gather form.
-//   tables: for every output index d its source index i0[d] and weight l1[d]; for every intermediate index m
-//           the contiguous range [dlo[m], dhi[m]] of output indices that touch it (same table for both axes).
 //   pass A: H[y][i] = sum_x wx(x,i) g_out[y][x]   for the output rows this band of intermediate rows needs
 //   pass B: G[j][i] = sum_y wy(y,j) H[y][i]       plus the sample position of (j,i) for the next kernel
 template <int C>
@@ -232,11 +288,9 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_mid_kernel(const float* _
   const int j0 = blockIdx.x * PCL_JR;
   if (j0 >= s) return;
   const int j1 = min(j0 + PCL_JR, s) - 1;
-  int* ti0 = reinterpret_cast<int*>(sm);     // [R]
-  float* tl1 = sm + R;                       // [R]
-  int* dlo = reinterpret_cast<int*>(sm + 2 * R);  // [R]  (s <= R on this path)
-  int* dhi = dlo + R;                        // [R]
-  float* H = sm + 4 * R;                     // [C][nrows][s]
+  float* tl1 = sm;                                   // [R]
+  int* start = reinterpret_cast<int*>(sm + R);       // [R+1]  (s <= R on this path)
+  float* H = sm + 2 * R + 4;                         // [C][nrows][s]
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
   float2* POS = reinterpret_cast<float2*>(base + 4 * (size_t)s * s);
@@ -244,64 +298,60 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_mid_kernel(const float* _
   const float Rf = (float)R;
   const float inv_s = 1.0f / (float)s;
   const bool fast = s <= R;
+  int ylo = 0, nrows = 0;
   if (fast) {
-    for (int m = threadIdx.x; m < s; m += PCL_THREADS) { dlo[m] = R; dhi[m] = -1; }
-    __syncthreads();
-    for (int d = threadIdx.x; d < R; d += PCL_THREADS) {
-      int i0, i1;
-      float l0, l1;
-      resize_coef(c, d, R, i0, i1, l0, l1);
-      ti0[d] = i0; tl1[d] = l1;
-      atomicMin(dlo + i0, d); atomicMax(dhi + i0, d);
-      atomicMin(dlo + i1, d); atomicMax(dhi + i1, d);
-    }
-    __syncthreads();
+    build_tables(c, R, tl1, start);
+    ylo = start[max(j0 - 1, 0)];
+    nrows = start[j1 + 1] - ylo;
   }
-  int ylo = 0, yhi = -1;
-  if (fast) { ylo = dlo[j0]; yhi = dhi[j1]; for (int j = j0; j <= j1; ++j) { ylo = min(ylo, dlo[j]); yhi = max(yhi, dhi[j]); } }
-  const int nrows = yhi - ylo + 1;
   if (fast && nrows > 0 && nrows * s <= cap) {
-    // pass A
     const int nA = nrows * s;
     for (int idx = threadIdx.x; idx < nA; idx += PCL_THREADS) {
       const int yr = fast_div(idx, s, inv_s), i = idx - yr * s;
-      const int y = ylo + yr;
       float acc[C];
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) acc[ch] = 0.f;
-      const float* row = go + (size_t)y * R;
-      const int xl = dlo[i], xh = dhi[i];
-      for (int x = xl; x <= xh; ++x) {
-        const int i0 = ti0[x];
-        const float l1 = tl1[x];
-        const int i1 = i0 + (i0 < s - 1 ? 1 : 0);
-        const float w = (i0 == i ? __fsub_rn(1.0f, l1) : 0.0f) + (i1 == i ? l1 : 0.0f);
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, __ldcs(row + (size_t)ch * R * R + x), acc[ch]);
-      }
+      transposed_taps<C, true>(go + (size_t)(ylo + yr) * R, (size_t)R * R, tl1, start, i, s, acc);
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) H[(ch * nrows + yr) * s + i] = acc[ch];
     }
     __syncthreads();
-    // pass B
     const int nB = (j1 - j0 + 1) * s;
     for (int idx = threadIdx.x; idx < nB; idx += PCL_THREADS) {
       const int jr = fast_div(idx, s, inv_s), i = idx - jr * s;
       const int j = j0 + jr;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const int yl = dlo[j], yh = dhi[j];
-      for (int y = yl; y <= yh; ++y) {
-        const int i0 = ti0[y];
-        const float l1 = tl1[y];
-        const int i1 = i0 + (i0 < s - 1 ? 1 : 0);
-        const float w = (i0 == j ? __fsub_rn(1.0f, l1) : 0.0f) + (i1 == j ? l1 : 0.0f);
+      // reduce along y: element d of the "line" is H[.][d - ylo][i]; walk it with stride s
+      float acc[C];
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+      for (int ch = 0; ch < C; ++ch) acc[ch] = 0.f;
+      {
+        const int a0 = start[j], a1 = start[j + 1];
+        for (int y = a0; y < a1; ++y) {
+          const float w = 1.0f - tl1[y];
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+        }
+        const int b0 = j > 0 ? start[j - 1] : a0;
+        for (int y = b0; y < a0; ++y) {
+          const float w = tl1[y];
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+        }
+        if (j == s - 1) {
+          for (int y = a0; y < a1; ++y) {
+            const float w = tl1[y];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+          }
+        }
       }
       float ix, iy;
-      sample_pos(c, j, i, Rf, ix, iy);
+      sample_pos_fast(c, j, i, Rf, ix, iy);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) v[ch] = acc[ch];
       POS[(size_t)j * s + i] = make_float2(ix, iy);
-      G[(size_t)j * s + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      G[(size_t)j * s + i] = make_float4(v[0], v[1], v[2], v[3]);
     }
     return;
   }
@@ -328,28 +378,29 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_mid_kernel(const float* _
       }
     }
     float ix, iy;
-    sample_pos(c, j, i, Rf, ix, iy);
+    sample_pos_fast(c, j, i, Rf, ix, iy);
     POS[(size_t)j * s + i] = make_float2(ix, iy);
     G[(size_t)j * s + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
 constexpr int PCL_TS = 32;              // source tile side
-constexpr int PCL_HALO = PCL_TS + 2;
-constexpr int PCL_REGCAP = 1600;        // intermediate pixels staged in smem per (tile, crop)
+constexpr int PCL_CELLS = PCL_TS + 1;   // cells = floor(sample position) in [tile-1, tile+31]
+constexpr int PCL_K = 8;                // list capacity per cell
 
 // Transposed grid_sample, gather form.  One CTA per (image, 32x32 source tile); for each crop of the image:
-// the inverse homography maps the tile (plus a one-pixel halo) into the intermediate grid; that region's
-// sample positions and gradients are staged in shared memory; every source pixel then collects from the
-// intermediate pixels inside the pre-image of its +-1 neighbourhood whose bilinear footprint covers it.
+//   1. the tile's pre-image under the inverse homography bounds a region of the intermediate grid;
+//   2. every intermediate pixel of the region is binned by floor(sample position) into per-cell lists in
+//      shared memory (integer atomics claim the slots);
+//   3. every source pixel reads the <= 4 cells whose bilinear footprint covers it and accumulates exactly its
+//      contributors, in index order (so the result does not depend on the order the atomics ran in).
+// g_img is written once per pixel: no float atomics, no memset.
 template <int C>
 __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R, float* __restrict__ g_img) {
-  __shared__ float2 pm[PCL_HALO * PCL_HALO];
-  __shared__ __align__(16) float4 gS[PCL_REGCAP];
-  __shared__ float2 pS[PCL_REGCAP];
-  __shared__ int box[4];  // i_min, i_max, j_min, j_max of the tile's pre-image (ints after floor/ceil)
-  __shared__ int anybad;
+  __shared__ int cnt[PCL_CELLS * PCL_CELLS];
+  __shared__ int lst[PCL_CELLS * PCL_CELLS * PCL_K];
+  __shared__ int overflow;
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
   const int im = img_base + blockIdx.y;
@@ -370,93 +421,96 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* _
     const float4* G = reinterpret_cast<const float4*>(base);
     const float2* POS = reinterpret_cast<const float2*>(base + 4 * (size_t)s * s);
     const float sm1 = (float)(s - 1);
-    __syncthreads();  // previous crop's readers are done with the shared tiles
-    if (threadIdx.x == 0) { box[0] = INT_MAX; box[1] = INT_MIN; box[2] = INT_MAX; box[3] = INT_MIN; anybad = 0; }
-    __syncthreads();
-    {
-      int imin = INT_MAX, imax = INT_MIN, jmin = INT_MAX, jmax = INT_MIN, bad = 0;
-      for (int idx = threadIdx.x; idx < PCL_HALO * PCL_HALO; idx += PCL_THREADS) {
-        const int hy = idx / PCL_HALO, hx = idx - hy * PCL_HALO;
-        // sample position equal to pixel index (px,py)  <=>  grid-sample pixel coordinate px + 0.5
-        const float gx = (float)(tx0 - 1 + hx) + 0.5f, gy = (float)(ty0 - 1 + hy) + 0.5f;
+    // 1. region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
+    //    sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5)
+    float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
+    bool bad = false;
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx) {
+        const float gx = (float)tx0 - 0.5f + 33.0f * cx, gy = (float)ty0 - 0.5f + 33.0f * cy;
         const float U = Pi[0] * gx + Pi[1] * gy + Pi[2];
         const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
         const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
-        float mi, mj;
         if (Wd > 1e-12f) {
           const float iw = 1.0f / Wd;
-          mi = fminf(fmaxf(U * iw * sm1, -4.0f), sm1 + 4.0f);
-          mj = fminf(fmaxf(V * iw * sm1, -4.0f), sm1 + 4.0f);
-          imin = min(imin, (int)floorf(mi - 0.05f)); imax = max(imax, (int)ceilf(mi + 0.05f));
-          jmin = min(jmin, (int)floorf(mj - 0.05f)); jmax = max(jmax, (int)ceilf(mj + 0.05f));
-        } else { mi = nanf(""); mj = nanf(""); bad = 1; }
-        pm[idx] = make_float2(mi, mj);
+          const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
+          ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
+        } else bad = true;
       }
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) {
-        imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, m)); imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, m));
-        jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, m)); jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, m));
-        bad |= __shfl_xor_sync(0xffffffffu, bad, m);
-      }
-      if (lx == 0) {
-        atomicMin(&box[0], imin); atomicMax(&box[1], imax); atomicMin(&box[2], jmin); atomicMax(&box[3], jmax);
-        if (bad) atomicOr(&anybad, 1);
-      }
-    }
-    __syncthreads();
     int ri0, ri1, rj0, rj1;
-    if (anybad) { ri0 = 0; ri1 = s - 1; rj0 = 0; rj1 = s - 1; }
-    else { ri0 = max(box[0], 0); ri1 = min(box[1], s - 1); rj0 = max(box[2], 0); rj1 = min(box[3], s - 1); }
-    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
+    if (bad) { ri0 = 0; ri1 = s - 1; rj0 = 0; rj1 = s - 1; }
+    else {
+      ri0 = max(0, (int)floorf(ilo - 0.25f)); ri1 = min(s - 1, (int)ceilf(ihi + 0.25f));
+      rj0 = max(0, (int)floorf(jlo - 0.25f)); rj1 = min(s - 1, (int)ceilf(jhi + 0.25f));
+    }
+    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (same decision in every thread)
     const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
-    const bool in_smem = rw * rh <= PCL_REGCAP;
-    if (in_smem) {
+    __syncthreads();  // previous crop's readers are done with cnt/lst
+    for (int idx = threadIdx.x; idx < PCL_CELLS * PCL_CELLS; idx += PCL_THREADS) cnt[idx] = 0;
+    if (threadIdx.x == 0) overflow = 0;
+    __syncthreads();
+    // 2. binning
+    {
       const float inv_rw = 1.0f / (float)rw;
+      const float cx_lo = (float)(tx0 - 1), cy_lo = (float)(ty0 - 1);
       for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
         const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
-        const size_t gidx = (size_t)(rj0 + rr) * s + (ri0 + cc);
-        pS[idx] = __ldg(POS + gidx);
-        gS[idx] = __ldg(G + gidx);
+        const int gidx = (rj0 + rr) * s + (ri0 + cc);
+        const float2 p = __ldg(POS + gidx);
+        const float fx = floorf(p.x) - cx_lo, fy = floorf(p.y) - cy_lo;
+        if (fx >= 0.0f && fx < (float)PCL_CELLS && fy >= 0.0f && fy < (float)PCL_CELLS) {
+          const int cell = (int)fy * PCL_CELLS + (int)fx;
+          const int slot = atomicAdd(&cnt[cell], 1);
+          if (slot < PCL_K) lst[cell * PCL_K + slot] = gidx; else overflow = 1;
+        }
       }
     }
     __syncthreads();
+    const bool slow = overflow != 0;
+    // 3. gather
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int ly = lyb + 8 * r;
       const int sx = tx0 + lx, sy = ty0 + ly;
       if (sx >= R || sy >= R) continue;
-      float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
-      bool bad = false;
-#pragma unroll
-      for (int dy = 0; dy <= 2; dy += 2)
-#pragma unroll
-        for (int dx = 0; dx <= 2; dx += 2) {
-          const float2 p = pm[(ly + dy) * PCL_HALO + (lx + dx)];
-          bad |= !(p.x == p.x);
-          ilo = fminf(ilo, p.x); ihi = fmaxf(ihi, p.x); jlo = fminf(jlo, p.y); jhi = fmaxf(jhi, p.y);
-        }
-      int i0, i1, j0, j1;
-      if (bad) { i0 = ri0; i1 = ri1; j0 = rj0; j1 = rj1; }
-      else {
-        i0 = max(ri0, (int)floorf(ilo - 0.05f)); i1 = min(ri1, (int)ceilf(ihi + 0.05f));
-        j0 = max(rj0, (int)floorf(jlo - 0.05f)); j1 = min(rj1, (int)ceilf(jhi + 0.05f));
-      }
       const float fsx = (float)sx, fsy = (float)sy;
-      for (int j = j0; j <= j1; ++j)
-        for (int i = i0; i <= i1; ++i) {
-          const int lidx = (j - rj0) * rw + (i - ri0);
-          const float2 p = in_smem ? pS[lidx] : __ldg(POS + (size_t)j * s + i);
-          const float dx = p.x - fsx, dy = p.y - fsy;   // exact (pixel indices are small integers)
-          if (!(dx > -1.0f && dx < 1.0f && dy > -1.0f && dy < 1.0f)) continue;
-          // forward weights: tap at floor(p): (floor+1) - p ; tap at floor(p)+1: p - floor
-          const float wx = dx >= 0.0f ? __fsub_rn(__fadd_rn(fsx, 1.0f), p.x) : __fsub_rn(p.x, __fsub_rn(fsx, 1.0f));
-          const float wy = dy >= 0.0f ? __fsub_rn(__fadd_rn(fsy, 1.0f), p.y) : __fsub_rn(p.y, __fsub_rn(fsy, 1.0f));
-          const float w = __fmul_rn(wx, wy);
-          const float4 g = in_smem ? gS[lidx] : __ldg(G + (size_t)j * s + i);
-          const float gv[4] = {g.x, g.y, g.z, g.w};
+      if (!slow) {
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) acc[r][ch] = fmaf(w, gv[ch], acc[r][ch]);
-        }
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int cell = (ly + dy) * PCL_CELLS + (lx + dx);  // floor(pos) == (sx-1+dx, sy-1+dy)
+            const int n = cnt[cell];
+            int prev = -1;
+            for (int e = 0; e < n; ++e) {
+              // next entry in increasing index order (lists are tiny: n is 1 or 2 almost always)
+              int cur = INT_MAX;
+              for (int f = 0; f < n; ++f) { const int v = lst[cell * PCL_K + f]; if (v > prev && v < cur) cur = v; }
+              prev = cur;
+              const float2 p = __ldg(POS + cur);
+              const float4 g = __ldg(G + cur);
+              const float w = (1.0f - fabsf(p.x - fsx)) * (1.0f - fabsf(p.y - fsy));
+              const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) acc[r][ch] = fmaf(w, gv[ch], acc[r][ch]);
+            }
+          }
+      } else {
+        // a cell list overflowed (extreme foreshortening): scan the whole region for this tile and crop
+        for (int j = rj0; j <= rj1; ++j)
+          for (int i = ri0; i <= ri1; ++i) {
+            const float2 p = __ldg(POS + (size_t)j * s + i);
+            const float ax = fabsf(p.x - fsx), ay = fabsf(p.y - fsy);
+            if (!(ax < 1.0f && ay < 1.0f)) continue;
+            const float4 g = __ldg(G + (size_t)j * s + i);
+            const float w = (1.0f - ax) * (1.0f - ay);
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) acc[r][ch] = fmaf(w, gv[ch], acc[r][ch]);
+          }
+      }
     }
   }
 #pragma unroll
@@ -520,7 +574,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   if (rc) return rc;
   // pass-A tile capacity: rows*s <= PCL_JR*(R-1)*s/(s-1) + 3s  
   const int cap = PCL_JR * R * 17 / 16 + 3 * R + 64;
-  const size_t smem_mid = sizeof(float) * ((size_t)4 * R + (size_t)C * cap);
+  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + (size_t)C * cap);
   HB_CUDA(cudaFuncSetAttribute(pcl_bwd_mid_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
   for (int ch = 0; ch < n_chunks; ++ch) {
