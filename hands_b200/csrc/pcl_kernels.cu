@@ -14,6 +14,7 @@
 // by bit-comparing a numpy emulation against torch 2.11 single-threaded ("PCL exactness").
 #include <climits>
 #include "hb_common.cuh"
+#include "tma.cuh"
 
 namespace hb {
 
@@ -215,6 +216,7 @@ __global__ void pcl_offsets_kernel(float* __restrict__ params, int n_crops, int 
 }
 
 constexpr int PCL_JR = 16;  // intermediate rows per CTA
+constexpr int PCL_RB = 2;   // output rows per bulk-copy stage of the transposed resize
 
 // approximate sample position for the backward pass (the gradient is continuous in the position, so the
 // correctly-rounded divisions of the forward are not needed here)
@@ -274,12 +276,21 @@ __device__ __forceinline__ void transposed_taps(const float* __restrict__ src, s
   }
 }
 
-// Transposed resize (g_out -> intermediate gradient), separable, gather form.
-//   pass A: H[y][i] = sum_x wx(x,i) g_out[y][x]   for the output rows this band of intermediate rows needs
-//   pass B: G[j][i] = sum_y wy(y,j) H[y][i]       plus the sample position of (j,i) for the next kernel
+// Transposed resize (g_out -> intermediate gradient), streaming form.
+// One CTA (PCL_MT threads) per (crop, band of PCL_JR intermediate rows).  The output rows the band needs are
+// streamed through a PCL_NS-stage shared-memory ring by bulk copies (one elected thread issues them, an mbarrier
+// per stage completes on the byte count).  Thread = intermediate column i: for each streamed row y it forms
+//   h = sum_{x in window(i)} wx(x,i) g_out[y][x]        (window = run(i-1) U run(i), contiguous)
+// and adds (1-l1[y]) h to the accumulator of intermediate row i0(y) and l1[y] h to the one of i0(y)+1; when a run
+// of y ends the finished row is written out together with its sample positions.  No intermediate buffer, no
+// second pass: every g_out element is read from DRAM once (band overlap re-reads hit L2).
+constexpr int PCL_MT = 64;   // threads per CTA
+constexpr int PCL_NS = 4;    // ring stages
+constexpr int PCL_NP = 4;    // columns per thread (s <= PCL_MT * PCL_NP on the fast path)
+
 template <int C>
-__global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
-                                                                  int q_base, int R, float* __restrict__ ws, int cap) {
+__global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
+                                                             int q_base, int R, float* __restrict__ ws, int use_tma) {
   extern __shared__ __align__(16) float sm[];
   const int q = q_base + blockIdx.y;
   const float* rec = params + (size_t)q * PF;
@@ -290,74 +301,124 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_mid_kernel(const float* _
   const int j1 = min(j0 + PCL_JR, s) - 1;
   float* tl1 = sm;                                   // [R]
   int* start = reinterpret_cast<int*>(sm + R);       // [R+1]  (s <= R on this path)
-  float* H = sm + 2 * R + 4;                         // [C][nrows][s]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * R + 4);   // [PCL_NS]
+  float* stage = sm + 2 * R + 4 + 2 * PCL_NS;        // [PCL_NS][C][PCL_RB][R]  (16-byte aligned when R % 4 == 0)
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
   float2* POS = reinterpret_cast<float2*>(base + 4 * (size_t)s * s);
   const float* go = g_out + (size_t)q * C * R * R;
   const float Rf = (float)R;
-  const float inv_s = 1.0f / (float)s;
-  const bool fast = s <= R;
-  int ylo = 0, nrows = 0;
-  if (fast) {
-    build_tables(c, R, tl1, start);
-    ylo = start[max(j0 - 1, 0)];
-    nrows = start[j1 + 1] - ylo;
-  }
-  if (fast && nrows > 0 && nrows * s <= cap) {
-    const int nA = nrows * s;
-    for (int idx = threadIdx.x; idx < nA; idx += PCL_THREADS) {
-      const int yr = fast_div(idx, s, inv_s), i = idx - yr * s;
-      float acc[C];
+  const int tid = threadIdx.x;
+  if (s <= R && s <= PCL_MT * PCL_NP && use_tma) {
+    if (tid == 0) {
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) acc[ch] = 0.f;
-      transposed_taps<C, true>(go + (size_t)(ylo + yr) * R, (size_t)R * R, tl1, start, i, s, acc);
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) H[(ch * nrows + yr) * s + i] = acc[ch];
+      for (int k = 0; k < PCL_NS; ++k) mbar_init(&bars[k], 1);
+      mbar_fence_init();
     }
-    __syncthreads();
-    const int nB = (j1 - j0 + 1) * s;
-    for (int idx = threadIdx.x; idx < nB; idx += PCL_THREADS) {
-      const int jr = fast_div(idx, s, inv_s), i = idx - jr * s;
-      const int j = j0 + jr;
-      // reduce along y: element d of the "line" is H[.][d - ylo][i]; walk it with stride s
-      float acc[C];
+    build_tables(c, R, tl1, start);   // contains the __syncthreads() that publishes the barrier init
+    const int jfirst = max(j0 - 1, 0);
+    const int ylo = start[jfirst], yhi = start[j1 + 1];
+    const int nrows = yhi - ylo;
+    const int nblk = (nrows + PCL_RB - 1) / PCL_RB;
+    auto issue = [&](int b) {
+      const int r0 = b * PCL_RB, nr = min(PCL_RB, nrows - r0);
+      const int st = b % PCL_NS;
+      float* dst = stage + (size_t)st * C * PCL_RB * R;
+      const uint32_t bytes = (uint32_t)(nr * R * sizeof(float));
+      mbar_arrive_expect_tx(&bars[st], bytes * C);
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) acc[ch] = 0.f;
-      {
-        const int a0 = start[j], a1 = start[j + 1];
-        for (int y = a0; y < a1; ++y) {
-          const float w = 1.0f - tl1[y];
+      for (int ch = 0; ch < C; ++ch) bulk_g2s(dst + (size_t)ch * PCL_RB * R, go + ((size_t)ch * R + ylo + r0) * R, bytes, &bars[st]);
+    };
+    if (tid == 0) {
+      for (int b = 0; b < min(nblk, PCL_NS); ++b) issue(b);
+    }
+    // per-thread columns: window [wb, we) with the split point wa (d < wa: weight l1[d], else 1-l1[d]; the last
+    // column gets weight 1 on its own run because the upper source index is clamped there)
+    int wb[PCL_NP], wa[PCL_NP], we[PCL_NP];
+    float cur[PCL_NP][C], nxt[PCL_NP][C];
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+    for (int p = 0; p < PCL_NP; ++p) {
+      const int i = tid + p * PCL_MT;
+      const bool on = i < s;
+      wa[p] = on ? start[i] : 0;
+      we[p] = on ? start[i + 1] : 0;
+      wb[p] = on ? (i > 0 ? start[i - 1] : wa[p]) : 0;
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) { cur[p][ch] = 0.f; nxt[p][ch] = 0.f; }
+    }
+    int jc = jfirst;   // intermediate row the accumulators `cur` belong to (`nxt` belongs to jc+1)
+    auto emit = [&](int j) {
+      if (j < j0 || j > j1) return;
+#pragma unroll
+      for (int p = 0; p < PCL_NP; ++p) {
+        const int i = tid + p * PCL_MT;
+        if (i < s) {
+          float ix, iy;
+          sample_pos_fast(c, j, i, Rf, ix, iy);
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) v[ch] = cur[p][ch];
+          POS[(size_t)j * s + i] = make_float2(ix, iy);
+          G[(size_t)j * s + i] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        const int b0 = j > 0 ? start[j - 1] : a0;
-        for (int y = b0; y < a0; ++y) {
-          const float w = tl1[y];
+      }
+    };
+    for (int b = 0; b < nblk; ++b) {
+      const int stg = b % PCL_NS;
+      mbar_wait(&bars[stg], (b / PCL_NS) & 1);
+      const float* st = stage + (size_t)stg * C * PCL_RB * R;
+      const int r0 = b * PCL_RB, nr = min(PCL_RB, nrows - r0);
+      for (int rr = 0; rr < nr; ++rr) {
+        const int y = ylo + r0 + rr;
+        while (y >= start[jc + 1]) {   // run of jc finished (block-uniform)
+          emit(jc);
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+          for (int p = 0; p < PCL_NP; ++p)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) { cur[p][ch] = nxt[p][ch]; nxt[p][ch] = 0.f; }
+          ++jc;
         }
-        if (j == s - 1) {
-          for (int y = a0; y < a1; ++y) {
-            const float w = tl1[y];
+        const float ly1 = tl1[y];
+        const float ly0 = 1.0f - ly1;
+        const bool last_row = jc >= s - 1;
+        const float* row = st + (size_t)rr * R;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, H[(ch * nrows + (y - ylo)) * s + i], acc[ch]);
+        for (int p = 0; p < PCL_NP; ++p) {
+          if (tid + p * PCL_MT < s) {
+            float h[C];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) h[ch] = 0.f;
+            const bool last_col = tid + p * PCL_MT == s - 1;
+            for (int d = wb[p]; d < we[p]; ++d) {
+              const float l = tl1[d];
+              const float w = d < wa[p] ? l : (last_col ? 1.0f : 1.0f - l);
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, row[(size_t)ch * PCL_RB * R + d], h[ch]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              cur[p][ch] = fmaf(last_row ? 1.0f : ly0, h[ch], cur[p][ch]);
+              if (!last_row) nxt[p][ch] = fmaf(ly1, h[ch], nxt[p][ch]);
+            }
           }
         }
       }
-      float ix, iy;
-      sample_pos_fast(c, j, i, Rf, ix, iy);
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      __syncthreads();   // everyone is done reading this stage
+      if (tid == 0 && b + PCL_NS < nblk) { fence_proxy_async(); issue(b + PCL_NS); }
+    }
+    while (jc <= j1) {   // flush: the band's last rows (also covers a clamped last row whose own run is empty)
+      emit(jc);
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) v[ch] = acc[ch];
-      POS[(size_t)j * s + i] = make_float2(ix, iy);
-      G[(size_t)j * s + i] = make_float4(v[0], v[1], v[2], v[3]);
+      for (int p = 0; p < PCL_NP; ++p)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) { cur[p][ch] = nxt[p][ch]; nxt[p][ch] = 0.f; }
+      ++jc;
     }
     return;
   }
-  // generic path: direct 2-D gather per intermediate pixel
+  // generic path (s > R, very large s, or unaligned rows): direct 2-D gather per intermediate pixel
   const int nB = (j1 - j0 + 1) * s;
-  for (int idx = threadIdx.x; idx < nB; idx += PCL_THREADS) {
+  for (int idx = tid; idx < nB; idx += PCL_MT) {
     const int jr = idx / s, i = idx - jr * s;
     const int j = j0 + jr;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -383,6 +444,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_mid_kernel(const float* _
     G[(size_t)j * s + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
+
 
 constexpr int PCL_TS = 32;              // source tile side
 constexpr int PCL_CELLS = PCL_TS + 1;   // cells = floor(sample position) in [tile-1, tile+31]
@@ -469,6 +531,21 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* _
     }
     __syncthreads();
     const bool slow = overflow != 0;
+    // 2b. put every cell's list in index order (one thread per cell; lists hold 1-2 entries almost always),
+    //     so the accumulation order below does not depend on the order the atomics ran in
+    if (!slow) {
+      for (int cell = threadIdx.x; cell < PCL_CELLS * PCL_CELLS; cell += PCL_THREADS) {
+        const int n = cnt[cell];
+        int* l = lst + cell * PCL_K;
+        for (int a = 1; a < n; ++a) {
+          const int v = l[a];
+          int b = a - 1;
+          while (b >= 0 && l[b] > v) { l[b + 1] = l[b]; --b; }
+          l[b + 1] = v;
+        }
+      }
+    }
+    __syncthreads();
     // 3. gather
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -483,12 +560,8 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* _
           for (int dx = 0; dx < 2; ++dx) {
             const int cell = (ly + dy) * PCL_CELLS + (lx + dx);  // floor(pos) == (sx-1+dx, sy-1+dy)
             const int n = cnt[cell];
-            int prev = -1;
             for (int e = 0; e < n; ++e) {
-              // next entry in increasing index order (lists are tiny: n is 1 or 2 almost always)
-              int cur = INT_MAX;
-              for (int f = 0; f < n; ++f) { const int v = lst[cell * PCL_K + f]; if (v > prev && v < cur) cur = v; }
-              prev = cur;
+              const int cur = lst[cell * PCL_K + e];
               const float2 p = __ldg(POS + cur);
               const float4 g = __ldg(G + cur);
               const float w = (1.0f - fabsf(p.x - fsx)) * (1.0f - fabsf(p.y - fsy));
@@ -552,36 +625,45 @@ extern "C" int hb_pcl_fwd(const float* img, const float* params, int n_crops, in
   }
 }
 
-static const int kPclChunkImgs = 64;
+// The backward runs in chunks of images: per chunk, pcl_bwd_mid fills the workspace (intermediate gradient +
+// sample positions of the chunk's crops, packed) and pcl_bwd_img consumes it.  The chunk size follows from the
+// workspace the caller provides: any size >= one image's worth works; hb_pcl_bwd_workspace_bytes() recommends
+// kPclChunkImgs images per chunk (large launches; the packed region actually touched is ~27% of the capacity
+// for boxes of side U{56..168}).
+static const int kPclChunkImgs = 1024;
+
+static size_t pcl_ws_bytes_per_img(int crops_per_img, int img_res) {
+  return sizeof(float) * (size_t)crops_per_img * (((size_t)PCL_WS_FLOATS_PER_PX * img_res * img_res + 3) & ~(size_t)3);
+}
 
 extern "C" size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int C, int img_res) {
   (void)C;
   if (n_crops <= 0 || crops_per_img <= 0) return 0;
   const int n_imgs = n_crops / crops_per_img;
-  const int chunk_crops = (n_imgs < kPclChunkImgs ? n_imgs : kPclChunkImgs) * crops_per_img;
-  return sizeof(float) * (size_t)chunk_crops * (((size_t)PCL_WS_FLOATS_PER_PX * img_res * img_res + 3) & ~(size_t)3);
+  return (size_t)(n_imgs < kPclChunkImgs ? n_imgs : kPclChunkImgs) * pcl_ws_bytes_per_img(crops_per_img, img_res);
 }
 
 template <int C>
-static int launch_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int R, float* g_img, float* ws, cudaStream_t st) {
+static int launch_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int R, float* g_img, float* ws, size_t ws_bytes, cudaStream_t st) {
   const int n_imgs = n_crops / crops_per_img;
-  const int chunk_imgs = n_imgs < kPclChunkImgs ? n_imgs : kPclChunkImgs;
+  const size_t fit = ws_bytes / pcl_ws_bytes_per_img(crops_per_img, R);
+  const int chunk_imgs = (size_t)n_imgs < fit ? n_imgs : (int)fit;
   const int chunk_crops = chunk_imgs * crops_per_img;
   const int n_chunks = (n_imgs + chunk_imgs - 1) / chunk_imgs;
   pcl_offsets_kernel<<<n_chunks, 32, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops);
   g_launches++;
   int rc = check_launch("pcl_offsets_kernel");
   if (rc) return rc;
-  // pass-A tile capacity: rows*s <= PCL_JR*(R-1)*s/(s-1) + 3s  
-  const int cap = PCL_JR * R * 17 / 16 + 3 * R + 64;
-  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + (size_t)C * cap);
+  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + 2 * PCL_NS + (size_t)PCL_NS * C * PCL_RB * R);
+  // bulk copies need 16-byte aligned rows: R % 4 == 0 and a 16-byte aligned g_out
+  const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
   HB_CUDA(cudaFuncSetAttribute(pcl_bwd_mid_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int im0 = ch * chunk_imgs;
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
     dim3 g1((R + PCL_JR - 1) / PCL_JR, nim * crops_per_img);
-    pcl_bwd_mid_kernel<C><<<g1, PCL_THREADS, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, cap);
+    pcl_bwd_mid_kernel<C><<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
     g_launches++;
     rc = check_launch("pcl_bwd_mid_kernel");
     if (rc) return rc;
@@ -601,14 +683,14 @@ extern "C" int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, 
     set_error("hb_pcl_bwd: bad argument (1 <= C <= 4)"); return HB_E_ARG;
   }
   if (n_crops == 0) return 0;
-  if (workspace_bytes < hb_pcl_bwd_workspace_bytes(n_crops, crops_per_img, C, img_res)) { set_error("hb_pcl_bwd: workspace too small"); return HB_E_WORKSPACE; }
+  if (workspace_bytes < pcl_ws_bytes_per_img(crops_per_img, img_res)) { set_error("hb_pcl_bwd: workspace too small (need at least one image's worth: %zu bytes)", pcl_ws_bytes_per_img(crops_per_img, img_res)); return HB_E_WORKSPACE; }
   if (reinterpret_cast<uintptr_t>(workspace) & 15u) { set_error("hb_pcl_bwd: workspace must be 16-byte aligned"); return HB_E_ALIGN; }
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   switch (C) {
-    case 1: return launch_bwd<1>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, st);
-    case 2: return launch_bwd<2>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, st);
-    case 3: return launch_bwd<3>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, st);
-    default: return launch_bwd<4>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, st);
+    case 1: return launch_bwd<1>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
+    case 2: return launch_bwd<2>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
+    case 3: return launch_bwd<3>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
+    default: return launch_bwd<4>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
   }
 }

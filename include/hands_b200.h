@@ -125,7 +125,8 @@ int hb_pcl_homography_host(const int32_t* bbox_host, const float* K_host, int im
 int hb_pcl_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int C, int img_res,
                float* out, void* stream);
 /* Backward w.r.t. img (the grid is data).  g_out (n_crops,C,R,R) -> g_img (n_crops/crops_per_img,C,R,R),
- *   written exactly once (no atomics, deterministic).  workspace: hb_pcl_bwd_workspace_bytes(). */
+ *   written exactly once (no float atomics, deterministic).  The backward runs in chunks of images sized by the
+ *   workspace given: hb_pcl_bwd_workspace_bytes() is the recommended size, any size >= one image's worth works. */
 size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int C, int img_res);
 int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res,
                float* g_img, void* workspace, size_t workspace_bytes, void* stream);
