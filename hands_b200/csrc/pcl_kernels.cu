@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
   const float* src = img + (size_t)(q / crops_per_img) * C * R * R;
   float* dst = out + (size_t)q * C * R * R;
   const float Rf = (float)R;
+  const int plane = R * R;
   const bool staged = nrows <= max_rows && s <= R;
   if (staged) {
     const int n = nrows * s;
@@ -129,8 +130,29 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
       float ix, iy;
       sample_pos(c, jlo + jr, i, Rf, ix, iy);
       float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ix > -1.0f && ix < Rf && iy > -1.0f && iy < Rf) {
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, yy0 = (int)fy;
+        const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+        const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+        const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+        const bool xa = x0 >= 0, xb = x0 + 1 < R, ya = yy0 >= 0, yb = yy0 + 1 < R;
+        const int o00 = yy0 * R + x0;
+        const float* pl = src;
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) v[ch] = gather_bilinear(src + (size_t)ch * R * R, R, ix, iy);
+        for (int ch = 0; ch < C; ++ch) {
+          const float nw = (xa && ya) ? __ldg(pl + o00) : 0.0f;
+          const float ne = (xb && ya) ? __ldg(pl + o00 + 1) : 0.0f;
+          const float sw = (xa && yb) ? __ldg(pl + o00 + R) : 0.0f;
+          const float se = (xb && yb) ? __ldg(pl + o00 + R + 1) : 0.0f;
+          float acc = __fmul_rn(nw, wnw);
+          acc = fmaf(ne, wne, acc);
+          acc = fmaf(sw, wsw, acc);
+          acc = fmaf(se, wse, acc);
+          v[ch] = acc;
+          pl += plane;
+        }
+      }
       mid4[idx] = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
@@ -140,7 +162,8 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
       resize_coef(c, x, R, b0, b1, lx0, lx1);
       int ra = -1, rb = -1;  // intermediate rows currently held in (m00,m01) and (m10,m11)
       float4 m00 = make_float4(0, 0, 0, 0), m01 = m00, m10 = m00, m11 = m00;
-      for (int y = y0; y <= y1; ++y) {
+      float* op = dst + (size_t)y0 * R + x;
+      for (int y = y0; y <= y1; ++y, op += R) {
         int a0, a1;
         float ly0, ly1;
         resize_coef(c, y, R, a0, a1, ly0, ly1);
@@ -163,7 +186,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
           acc = fmaf(w00, a[ch], acc);
           acc = fmaf(w10, d[ch], acc);
           acc = fmaf(w11, e[ch], acc);
-          __stcs(dst + ((size_t)ch * R + y) * R + x, acc);
+          __stcs(op + ch * plane, acc);
         }
       }
     }
@@ -287,6 +310,7 @@ __device__ __forceinline__ void transposed_taps(const float* __restrict__ src, s
 constexpr int PCL_MT = 64;   // threads per CTA
 constexpr int PCL_NS = 4;    // ring stages
 constexpr int PCL_NP = 4;    // columns per thread (s <= PCL_MT * PCL_NP on the fast path)
+static_assert(PCL_RB == 2, "the streaming transposed resize processes the two rows of a stage together");
 
 template <int C>
 __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
@@ -368,39 +392,54 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
       mbar_wait(&bars[stg], (b / PCL_NS) & 1);
       const float* st = stage + (size_t)stg * C * PCL_RB * R;
       const int r0 = b * PCL_RB, nr = min(PCL_RB, nrows - r0);
-      for (int rr = 0; rr < nr; ++rr) {
-        const int y = ylo + r0 + rr;
-        while (y >= start[jc + 1]) {   // run of jc finished (block-uniform)
-          emit(jc);
+      // horizontal reduction of the block's (<= PCL_RB = 2) rows: weights and loop overhead are shared by the rows
+      float h[PCL_NP][2][C];
+#pragma unroll
+      for (int p = 0; p < PCL_NP; ++p) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) { h[p][0][ch] = 0.f; h[p][1][ch] = 0.f; }
+        if (tid + p * PCL_MT < s) {
+          const bool last_col = tid + p * PCL_MT == s - 1;
+          for (int d = wb[p]; d < wa[p]; ++d) {
+            const float w = tl1[d];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              h[p][0][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + d], h[p][0][ch]);
+              h[p][1][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + R + d], h[p][1][ch]);
+            }
+          }
+          for (int d = wa[p]; d < we[p]; ++d) {
+            const float w = last_col ? 1.0f : 1.0f - tl1[d];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              h[p][0][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + d], h[p][0][ch]);
+              h[p][1][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + R + d], h[p][1][ch]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < PCL_RB; ++rr) {
+        if (rr < nr) {
+          const int y = ylo + r0 + rr;
+          while (y >= start[jc + 1]) {   // run of jc finished (block-uniform)
+            emit(jc);
+#pragma unroll
+            for (int p = 0; p < PCL_NP; ++p)
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) { cur[p][ch] = nxt[p][ch]; nxt[p][ch] = 0.f; }
+            ++jc;
+          }
+          const float ly1 = tl1[y];
+          const bool last_row = jc >= s - 1;
+          const float ly0 = last_row ? 1.0f : 1.0f - ly1;
 #pragma unroll
           for (int p = 0; p < PCL_NP; ++p)
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) { cur[p][ch] = nxt[p][ch]; nxt[p][ch] = 0.f; }
-          ++jc;
-        }
-        const float ly1 = tl1[y];
-        const float ly0 = 1.0f - ly1;
-        const bool last_row = jc >= s - 1;
-        const float* row = st + (size_t)rr * R;
-#pragma unroll
-        for (int p = 0; p < PCL_NP; ++p) {
-          if (tid + p * PCL_MT < s) {
-            float h[C];
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) h[ch] = 0.f;
-            const bool last_col = tid + p * PCL_MT == s - 1;
-            for (int d = wb[p]; d < we[p]; ++d) {
-              const float l = tl1[d];
-              const float w = d < wa[p] ? l : (last_col ? 1.0f : 1.0f - l);
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, row[(size_t)ch * PCL_RB * R + d], h[ch]);
-            }
-#pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-              cur[p][ch] = fmaf(last_row ? 1.0f : ly0, h[ch], cur[p][ch]);
-              if (!last_row) nxt[p][ch] = fmaf(ly1, h[ch], nxt[p][ch]);
+              cur[p][ch] = fmaf(ly0, h[p][rr][ch], cur[p][ch]);
+              if (!last_row) nxt[p][ch] = fmaf(ly1, h[p][rr][ch], nxt[p][ch]);
             }
-          }
         }
       }
       __syncthreads();   // everyone is done reading this stage
@@ -458,7 +497,7 @@ constexpr int PCL_K = 8;                // list capacity per cell
 //      contributors, in index order (so the result does not depend on the order the atomics ran in).
 // g_img is written once per pixel: no float atomics, no memset.
 template <int C>
-__global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
+__global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R, float* __restrict__ g_img) {
   __shared__ int cnt[PCL_CELLS * PCL_CELLS];
   __shared__ int lst[PCL_CELLS * PCL_CELLS * PCL_K];
@@ -475,6 +514,9 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* _
   for (int k = 0; k < crops_per_img; ++k) {
     const int q = im * crops_per_img + k;
     const float* rec = params + (size_t)q * PF;
+    // cheap cull: the crop's footprint box (from the setup kernel) against this tile
+    if (__float_as_int(__ldg(rec + 22)) > tx0 + PCL_TS || __float_as_int(__ldg(rec + 23)) < tx0 - 1 ||
+        __float_as_int(__ldg(rec + 24)) > ty0 + PCL_TS || __float_as_int(__ldg(rec + 25)) < ty0 - 1) continue;
     const int s = __float_as_int(__ldg(rec + 18));
     float Pi[9];
 #pragma unroll
@@ -496,7 +538,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* _
         const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
         const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
         if (Wd > 1e-12f) {
-          const float iw = 1.0f / Wd;
+          const float iw = __frcp_rn(Wd);
           const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
           ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
         } else bad = true;
@@ -590,8 +632,9 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_bwd_img_kernel(const float* _
   for (int r = 0; r < 4; ++r) {
     const int sx = tx0 + lx, sy = ty0 + lyb + 8 * r;
     if (sx >= R || sy >= R) continue;
+    float* op = g_img + (size_t)im * C * R * R + sy * R + sx;
 #pragma unroll
-    for (int ch = 0; ch < C; ++ch) __stcs(g_img + (((size_t)im * C + ch) * R + sy) * R + sx, acc[r][ch]);
+    for (int ch = 0; ch < C; ++ch) __stcs(op + ch * R * R, acc[r][ch]);
   }
 }
 

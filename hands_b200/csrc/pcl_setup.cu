@@ -76,8 +76,28 @@ __global__ void pcl_setup_kernel(const int32_t* __restrict__ bbox, const float* 
   rec[19] = img_res > 1 ? __fdiv_rn((float)(s - 1), (float)(img_res - 1)) : 0.0f;
   rec[20] = s > 1 ? __fdiv_rn(1.0f, (float)(s - 1)) : 0.0f;
   rec[21] = __int_as_float(0);
+  // source-pixel bounding box of the crop's bilinear footprint (corners of the unit square under P; a
+  // homography maps the square to a convex quad, so the corner box bounds it) -- used to cull source tiles
+  int fx0 = 0, fx1 = img_res - 1, fy0 = 0, fy1 = img_res - 1;
+  {
+    double xmin = 1e30, xmax = -1e30, ymin = 1e30, ymax = -1e30;
+    bool ok = true;
+    for (int cy = 0; cy < 2; ++cy)
+      for (int cx = 0; cx < 2; ++cx) {
+        const double X = Pf[0] * cx + Pf[1] * cy + Pf[2], Y = Pf[3] * cx + Pf[4] * cy + Pf[5], Z = Pf[6] * cx + Pf[7] * cy + Pf[8];
+        if (!(Z > 1e-9)) { ok = false; continue; }
+        const double ix = X / Z - 0.5, iy = Y / Z - 0.5;
+        xmin = fmin(xmin, ix); xmax = fmax(xmax, ix); ymin = fmin(ymin, iy); ymax = fmax(ymax, iy);
+      }
+    if (ok) {
+      xmin = fmax(xmin - 1.5, -4.0); ymin = fmax(ymin - 1.5, -4.0);
+      xmax = fmin(xmax + 2.5, (double)img_res + 4.0); ymax = fmin(ymax + 2.5, (double)img_res + 4.0);
+      fx0 = (int)floor(xmin); fx1 = (int)ceil(xmax); fy0 = (int)floor(ymin); fy1 = (int)ceil(ymax);
+    }
+  }
+  rec[22] = __int_as_float(fx0); rec[23] = __int_as_float(fx1); rec[24] = __int_as_float(fy0); rec[25] = __int_as_float(fy1);
 #pragma unroll
-  for (int k = 22; k < PF; ++k) rec[k] = 0.0f;
+  for (int k = 26; k < PF; ++k) rec[k] = 0.0f;
   if (Rout) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rout[(size_t)q * 9 + k] = (float)Rv[k];
