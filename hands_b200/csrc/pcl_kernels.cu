@@ -225,16 +225,39 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
 // gradient (channels in x,y,z,w), then POS float2[s*s] sample positions.  6*s*s floats per crop.
 constexpr int PCL_WS_FLOATS_PER_PX = 6;
 
-__global__ void pcl_offsets_kernel(float* __restrict__ params, int n_crops, int chunk_crops) {
-  if (threadIdx.x != 0) return;
+// exclusive scan of the per-crop workspace sizes inside each chunk (one 1024-thread block per chunk)
+__global__ void __launch_bounds__(1024) pcl_offsets_kernel(float* __restrict__ params, int n_crops, int chunk_crops) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
   const int q0 = blockIdx.x * chunk_crops;
   const int q1 = min(q0 + chunk_crops, n_crops);
-  int off = 0;
-  for (int q = q0; q < q1; ++q) {
-    float* rec = params + (size_t)q * PF;
-    const int s = __float_as_int(rec[18]);
-    rec[21] = __int_as_float(off);
-    off += (PCL_WS_FLOATS_PER_PX * s * s + 3) & ~3;  // keep every crop's float4 array 16-byte aligned
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = q0; base < q1; base += 1024) {
+    const int q = base + threadIdx.x;
+    int sz = 0;
+    if (q < q1) {
+      const int s = __float_as_int(params[(size_t)q * PF + 18]);
+      sz = (PCL_WS_FLOATS_PER_PX * s * s + 3) & ~3;  // keep every crop's float4 array 16-byte aligned
+    }
+    int inc = sz;  // inclusive scan within the warp
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, m); if (lane >= m) inc += t; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, m); if (lane >= m) t += u; }
+      warp_tot[lane] = t;  // inclusive totals of the warps
+    }
+    __syncthreads();
+    const int before = carry + (wid > 0 ? warp_tot[wid - 1] : 0) + inc - sz;
+    if (q < q1) params[(size_t)q * PF + 21] = __int_as_float(before);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + sz;
+    __syncthreads();
   }
 }
 
@@ -693,7 +716,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const int chunk_imgs = (size_t)n_imgs < fit ? n_imgs : (int)fit;
   const int chunk_crops = chunk_imgs * crops_per_img;
   const int n_chunks = (n_imgs + chunk_imgs - 1) / chunk_imgs;
-  pcl_offsets_kernel<<<n_chunks, 32, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops);
+  pcl_offsets_kernel<<<n_chunks, 1024, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops);
   g_launches++;
   int rc = check_launch("pcl_offsets_kernel");
   if (rc) return rc;
