@@ -44,15 +44,24 @@ __device__ __forceinline__ float lin01(const Crop& c, int i) {
   return (i < c.s / 2) ? __fmul_rn(c.step, (float)i) : fmaf(-c.step, (float)(c.s - 1 - i), 1.0f);
 }
 
+// Correctly rounded a / b for a constant b with rb = RN(1/b) (Markstein's sequence: q = RN(a*rb),
+// r = a - b*q exactly by FMA, RN(q + r*rb) == RN(a/b) for normal results) -- 3 instructions instead of an
+// IEEE division; bit-identical to `a / b`.
+__device__ __forceinline__ float div_by_const(float a, float b, float rb) {
+  const float q = __fmul_rn(a, rb);
+  const float r = fmaf(-b, q, a);
+  return fmaf(r, rb, q);
+}
+
 // source-image sample position (in pixel-index units) of intermediate pixel (row j, col i)
-__device__ __forceinline__ void sample_pos(const Crop& c, int j, int i, float R, float& ix, float& iy) {
+__device__ __forceinline__ void sample_pos(const Crop& c, int j, int i, float R, float rcpR, float& ix, float& iy) {
   const float u = lin01(c, i), v = lin01(c, j);
   const float X = __fadd_rn(fmaf(c.P[1], v, __fmul_rn(c.P[0], u)), c.P[2]);
   const float Y = __fadd_rn(fmaf(c.P[4], v, __fmul_rn(c.P[3], u)), c.P[5]);
   const float Z = __fadd_rn(fmaf(c.P[7], v, __fmul_rn(c.P[6], u)), c.P[8]);
   const float den = __fadd_rn(1e-8f, Z);
-  const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fdiv_rn(X, den), R), 2.0f), 1.0f);
-  const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fdiv_rn(Y, den), R), 2.0f), 1.0f);
+  const float gx = __fsub_rn(__fmul_rn(div_by_const(__fdiv_rn(X, den), R, rcpR), 2.0f), 1.0f);
+  const float gy = __fsub_rn(__fmul_rn(div_by_const(__fdiv_rn(Y, den), R, rcpR), 2.0f), 1.0f);
   const float half = R * 0.5f;
   ix = fmaf(__fadd_rn(gx, 1.0f), half, -0.5f);
   iy = fmaf(__fadd_rn(gy, 1.0f), half, -0.5f);
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
   const float* src = img + (size_t)(q / crops_per_img) * C * R * R;
   float* dst = out + (size_t)q * C * R * R;
   const float Rf = (float)R;
+  const float rcpR = __fdiv_rn(1.0f, Rf);
   const int plane = R * R;
   const bool staged = nrows <= max_rows && s <= R;
   if (staged) {
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
     for (int idx = threadIdx.x; idx < n; idx += PCL_THREADS) {
       const int jr = fast_div(idx, s, inv_s), i = idx - jr * s;
       float ix, iy;
-      sample_pos(c, jlo + jr, i, Rf, ix, iy);
+      sample_pos(c, jlo + jr, i, Rf, rcpR, ix, iy);
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (ix > -1.0f && ix < Rf && iy > -1.0f && iy < Rf) {
         const float fx = floorf(ix), fy = floorf(iy);
@@ -160,33 +170,36 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
       int b0, b1;
       float lx0, lx1;
       resize_coef(c, x, R, b0, b1, lx0, lx1);
-      int ra = -1, rb = -1;  // intermediate rows currently held in (m00,m01) and (m10,m11)
-      float4 m00 = make_float4(0, 0, 0, 0), m01 = m00, m10 = m00, m11 = m00;
+      // s <= R here, so the source row index advances by 0 or 1 per output row: keep the two live intermediate
+      // rows in registers and shift when it advances (block-uniform control flow)
+      int a0, a1;
+      float ly0, ly1;
+      resize_coef(c, y0, R, a0, a1, ly0, ly1);
+      const float4* row = mid4 + (a0 - jlo) * s;
+      float4 m00 = row[b0], m01 = row[b1];
+      row = mid4 + (a1 - jlo) * s;
+      float4 m10 = row[b0], m11 = row[b1];
       float* op = dst + (size_t)y0 * R + x;
+#pragma unroll 1
       for (int y = y0; y <= y1; ++y, op += R) {
-        int a0, a1;
-        float ly0, ly1;
-        resize_coef(c, y, R, a0, a1, ly0, ly1);
-        if (a0 != ra) {
-          if (a0 == rb) { m00 = m10; m01 = m11; }
-          else { const float4* row = mid4 + (a0 - jlo) * s; m00 = row[b0]; m01 = row[b1]; }
-          ra = a0;
-        }
-        if (a1 != rb) {
-          if (a1 == ra) { m10 = m00; m11 = m01; }
-          else { const float4* row = mid4 + (a1 - jlo) * s; m10 = row[b0]; m11 = row[b1]; }
-          rb = a1;
-        }
         const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1), w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
-        const float a[4] = {m00.x, m00.y, m00.z, m00.w}, b[4] = {m01.x, m01.y, m01.z, m01.w};
-        const float d[4] = {m10.x, m10.y, m10.z, m10.w}, e[4] = {m11.x, m11.y, m11.z, m11.w};
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) {
-          float acc = __fmul_rn(w01, b[ch]);
-          acc = fmaf(w00, a[ch], acc);
-          acc = fmaf(w10, d[ch], acc);
-          acc = fmaf(w11, e[ch], acc);
-          __stcs(op + ch * plane, acc);
+        float o0 = __fmul_rn(w01, m01.x), o1 = __fmul_rn(w01, m01.y), o2 = __fmul_rn(w01, m01.z), o3 = __fmul_rn(w01, m01.w);
+        o0 = fmaf(w00, m00.x, o0); o1 = fmaf(w00, m00.y, o1); o2 = fmaf(w00, m00.z, o2); o3 = fmaf(w00, m00.w, o3);
+        o0 = fmaf(w10, m10.x, o0); o1 = fmaf(w10, m10.y, o1); o2 = fmaf(w10, m10.z, o2); o3 = fmaf(w10, m10.w, o3);
+        o0 = fmaf(w11, m11.x, o0); o1 = fmaf(w11, m11.y, o1); o2 = fmaf(w11, m11.z, o2); o3 = fmaf(w11, m11.w, o3);
+        __stcs(op, o0);
+        if (C > 1) __stcs(op + plane, o1);
+        if (C > 2) __stcs(op + 2 * plane, o2);
+        if (C > 3) __stcs(op + 3 * plane, o3);
+        if (y < y1) {
+          int n0, n1;
+          resize_coef(c, y + 1, R, n0, n1, ly0, ly1);
+          if (n0 != a0) {   // the source row advanced
+            if (n0 == a1) { m00 = m10; m01 = m11; }
+            else { const float4* nr = mid4 + (n0 - jlo) * s; m00 = nr[b0]; m01 = nr[b1]; }
+            if (n1 != a1) { const float4* nr = mid4 + (n1 - jlo) * s; m10 = nr[b0]; m11 = nr[b1]; }
+            a0 = n0; a1 = n1;
+          }
         }
       }
     }
@@ -204,10 +217,10 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
     resize_coef(c, x, R, b0, b1, lx0, lx1);
     const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1), w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
     float px[4], py[4];
-    sample_pos(c, a0, b0, Rf, px[0], py[0]);
-    sample_pos(c, a0, b1, Rf, px[1], py[1]);
-    sample_pos(c, a1, b0, Rf, px[2], py[2]);
-    sample_pos(c, a1, b1, Rf, px[3], py[3]);
+    sample_pos(c, a0, b0, Rf, rcpR, px[0], py[0]);
+    sample_pos(c, a0, b1, Rf, rcpR, px[1], py[1]);
+    sample_pos(c, a1, b0, Rf, rcpR, px[2], py[2]);
+    sample_pos(c, a1, b1, Rf, rcpR, px[3], py[3]);
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
       const float* pl = src + (size_t)ch * R * R;
