@@ -8,6 +8,7 @@
 namespace hb {
 
 std::atomic<uint64_t> g_launches{0};
+int g_mano_tc = -1;   // -1: not decided yet (env HB_MANO_TC, default on)
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -31,7 +32,8 @@ int check_launch(const char* what) {
 using namespace hb;
 
 extern "C" const char* hb_last_error_string(void) { return g_err; }
-extern "C" int hb_version(void) { return 100; }
+extern "C" int hb_version(void) { return 101; }
+extern "C" int hb_mano_set_tensor_core(int on) { const int prev = g_mano_tc; g_mano_tc = on ? 1 : 0; return prev; }
 extern "C" uint64_t hb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* J_regressor,
@@ -65,9 +67,10 @@ extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, c
   // host-side re-layout
   const size_t nPk = (size_t)NP * 3 * VP, nPt = (size_t)3 * VP * FS, nVt = (size_t)3 * VP, nWt = (size_t)NJ * VP, nWv = (size_t)VP * NJ;
   const size_t nJt = NJ * 3, nJsd = NJ * 3 * NB, nPm = 48;
+  const size_t nB = (size_t)10 * 19 * 240 * 8;   // tensor-core operand slabs
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 3) / 4 * 4; return o; };  // keep 16-byte alignment
-  const size_t oPk = take(nPk), oPt = take(nPt), oVt = take(nVt), oWt = take(nWt), oWv = take(nWv), oJt = take(nJt), oJsd = take(nJsd), oPm = take(nPm);
+  const size_t oPk = take(nPk), oPt = take(nPt), oVt = take(nVt), oWt = take(nWt), oWv = take(nWv), oJt = take(nJt), oJsd = take(nJsd), oPm = take(nPm), oBh = take(nB), oBl = take(nB);
   std::vector<float> hostbuf(off, 0.0f);
   float* Pk = hostbuf.data() + oPk; float* Pt = hostbuf.data() + oPt; float* Vt = hostbuf.data() + oVt;
   float* Wt = hostbuf.data() + oWt; float* Wv = hostbuf.data() + oWv; float* Jt = hostbuf.data() + oJt;
@@ -95,6 +98,23 @@ extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, c
       }
     }
   for (int k = 0; k < 48; ++k) Pm[k] = pose_mean[k];
+  // tensor-core B operand: column c' = k*800 + v (coordinate-major), tile = c'/240, UMMA K-major no-swizzle slabs
+  // [tile][k-step][k-half][row-group][row][4]; split into TF32 hi/lo parts
+  {
+    float* Bh = hostbuf.data() + oBh;
+    float* Bl = hostbuf.data() + oBl;
+    for (int tile = 0; tile < 10; ++tile)
+      for (int ks = 0; ks < 19; ++ks)
+        for (int n = 0; n < 240; ++n)
+          for (int kk = 0; kk < 8; ++kk) {
+            const int cp = tile * 240 + n, pidx = ks * 8 + kk;
+            const int k = cp / VP, v = cp % VP;
+            const float val = (pidx < NP && v < NV) ? Pk[((size_t)pidx * 3 + k) * VP + v] : 0.0f;
+            const float hi = tf32_round(val), lo = tf32_round(val - hi);
+            const size_t o = ((size_t)tile * 19 + ks) * 1920 + (size_t)(kk >> 2) * 960 + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
+            Bh[o] = hi; Bl[o] = lo;
+          }
+  }
 
   int prev = -1;
   HB_CUDA(cudaGetDevice(&prev));
@@ -109,7 +129,7 @@ extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, c
     return (int)e;
   }
   const float* d = (const float*)blob;
-  c.Pk = d + oPk; c.Pt = d + oPt; c.Vt = d + oVt; c.Wt = d + oWt; c.Wv = d + oWv; c.Jt = d + oJt; c.Jsd = d + oJsd; c.pose_mean = d + oPm;
+  c.Pk = d + oPk; c.Pt = d + oPt; c.Vt = d + oVt; c.Wt = d + oWt; c.Wv = d + oWv; c.Jt = d + oJt; c.Jsd = d + oJsd; c.pose_mean = d + oPm; c.Bhi = d + oBh; c.Blo = d + oBl;
   hb_mano* hm = new hb_mano;
   hm->c = c; hm->device = device; hm->blob = blob;
   *out = hm;

@@ -32,6 +32,8 @@ struct ManoConst {
   const float* Jt;    // [16][3]       J_regressor @ v_template           (fp64 fold)
   const float* Jsd;   // [16][3][10]   J_regressor @ shapedirs            (fp64 fold)
   const float* pose_mean;  // [48]
+  const float* Bhi;   // [10 tiles][19 k-steps][240 x 8] TF32 high parts of the stacked basis, UMMA slab order (mano_tc.cu)
+  const float* Blo;   // same, low parts
   int parents[NJ];
   int level[NJ];       // depth of each joint in the kinematic tree (root = 0)
   int child[NJ][5];    // child joints, -1 padded
@@ -51,6 +53,18 @@ int check_launch(const char* what);
       return (int)_e;                                                     \
     }                                                                     \
   } while (0)
+
+// TF32 split used by the tensor-core path: hi = x rounded to 10 mantissa bits, lo = (x - hi) rounded likewise
+__host__ __device__ inline float tf32_round(float x) {
+  union { float f; uint32_t u; } c;
+  c.f = x;
+  c.u = (c.u + 0x1000u) & 0xFFFFE000u;
+  return c.f;
+}
+
+size_t tc_smem_bytes();
+int launch_blend_tc(const float* Fhi, const float* Flo, const float* Bhi, const float* Blo, const float* vt, int B, float* vp, cudaStream_t st);
+extern int g_mano_tc;   // 1: blendshape contraction on tcgen05 (mano_tc.cu); 0: register-tiled FFMA
 
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 

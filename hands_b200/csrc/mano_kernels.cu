@@ -15,6 +15,7 @@
 //   A   [G][HBF][AS]      16 x (3x4) transforms
 //   OFF [G][HBF][8]       t1 (transl or 0), t2 (cam_t or 0), pad
 //   backward only: gF [NSLICE][G][HBF][FS], gA [NSLICE][G][HBF][AS], gO [NSLICE][G][HBF][8]
+#include <cstdlib>
 #include "hb_common.cuh"
 #include "pose_math.cuh"
 
@@ -29,6 +30,11 @@ __host__ __device__ inline size_t ws_gF(int B) { return ws_fwd_end(B); }
 __host__ __device__ inline size_t ws_gA(int B) { return ws_gF(B) + (size_t)NSLICE * ws_groups(B) * HBF * FS; }
 __host__ __device__ inline size_t ws_gO(int B) { return ws_gA(B) + (size_t)NSLICE * ws_groups(B) * HBF * AS; }
 __host__ __device__ inline size_t ws_bwd_end(int B) { return ws_gO(B) + (size_t)NSLICE * ws_groups(B) * HBF * 8; }
+// tensor-core path regions (after the FFMA regions): feature slabs hi/lo [G128][19][1024], v_posed [G128*128][2400]
+__host__ __device__ inline size_t ws_g128(int B) { return (size_t)(B + 127) / 128; }
+__host__ __device__ inline size_t ws_tc_base(int B, int backward) { return backward ? ws_bwd_end(B) : ws_fwd_end(B); }
+__host__ __device__ inline size_t ws_tc_F(int B) { return ws_g128(B) * 19 * 1024; }
+__host__ __device__ inline size_t ws_tc_end(int B, int backward) { return ws_tc_base(B, backward) + 2 * ws_tc_F(B) + ws_g128(B) * 128 * 2400; }
 
 // -------------------------------------------------------------------------------------------
 // per-(hand, joint) forward state
@@ -52,6 +58,7 @@ struct JointState {
 struct PoseArgs {
   const float* pose; int is_rotmat; const float* pre_rot; const float* betas;
   const float* cam; const float* K; const float* transl; int B; float img_res; float min_s;
+  float* fh; float* fl;   // tensor-core feature slabs (hi / lo TF32 parts) or NULL
 };
 
 __device__ __forceinline__ float shfl16(float v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
@@ -142,6 +149,22 @@ __global__ void __launch_bounds__(128) mano_pose_fwd_kernel(ManoConst c, PoseArg
   const size_t g = b / HBF, h = b % HBF;
   float* F = ws + ws_F(a.B) + g * FS * HBF;
   float* A = ws + ws_A(a.B) + (g * HBF + h) * AS + i * 12;
+  if (a.fh) {
+    // UMMA slab order: [group128][k-step][k-half][row-group][row][4]  (mano_tc.cu)
+    const size_t gb = (size_t)(b / 128) * 19 * 1024;
+    const int hl = b % 128;
+    const int rowoff = (hl >> 3) * 32 + (hl & 7) * 4;
+    const int p0 = i > 0 ? (i - 1) * 9 : NPF, np = i > 0 ? 9 : FS - NPF;
+    for (int k = 0; k < np; ++k) {
+      const int pidx = p0 + k;
+      float val;
+      if (i > 0) val = s.R[k] - ((k % 4 == 0) ? 1.f : 0.f);
+      else val = pidx < NP ? __ldg(a.betas + (size_t)b * NB + (pidx - NPF)) : 0.f;
+      const float hi = tf32_round(val), lo = tf32_round(val - hi);
+      const size_t o = gb + (size_t)(pidx >> 3) * 1024 + ((pidx >> 2) & 1) * 512 + rowoff + (pidx & 3);
+      a.fh[o] = hi; a.fl[o] = lo;
+    }
+  }
   if (i > 0) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) F[((i - 1) * 9 + k) * HBF + h] = s.R[k] - ((k % 4 == 0) ? 1.f : 0.f);
@@ -233,8 +256,9 @@ __device__ __forceinline__ void blend_transforms(const float* __restrict__ Ah, c
 
 struct SkinFwdOut { float* vertices; float* v3d; float* joints3d; float* j3d_cam; float* j2d; };
 
+template <bool USE_VP>
 __global__ void __launch_bounds__(VPB) mano_skin_fwd_kernel(ManoConst c, const float* __restrict__ ws, const float* __restrict__ Kmat,
-                                                            int B, float img_res, SkinFwdOut o) {
+                                                            int B, float img_res, SkinFwdOut o, const float* __restrict__ vp) {
   extern __shared__ __align__(16) float smem[];
   float* Fs = smem;                 // [FS][HBF]
   float* As = Fs + FS * HBF;        // [HBF][AS]
@@ -253,7 +277,15 @@ __global__ void __launch_bounds__(VPB) mano_skin_fwd_kernel(ManoConst c, const f
     for (int idx = tid; idx < HBF * 8 / 4; idx += VPB) reinterpret_cast<float4*>(Os)[idx] = srcO[idx];
   }
   __syncthreads();
-  {
+  if (USE_VP) {
+    // v_posed comes from the tensor-core kernel: [hand][k][800] coordinate-major, coalesced over vertices
+#pragma unroll 4
+    for (int h = 0; h < HBF; ++h) {
+      const int b = min(b0 + h, B - 1);
+      const float* src = vp + (size_t)b * (3 * VP) + v;
+      Xs[h * XS + 3 * tid + 0] = __ldg(src); Xs[h * XS + 3 * tid + 1] = __ldg(src + VP); Xs[h * XS + 3 * tid + 2] = __ldg(src + 2 * VP);
+    }
+  } else {
     float acc[HBF][3];
     blend_gemm(c, Fs, v, acc);
 #pragma unroll
@@ -319,8 +351,9 @@ struct SkinBwdIn { const float* g_vertices; const float* g_v3d; const float* g_j
 constexpr int HSUB = 8;           // hands per reduction pass of the backward kernel
 constexpr int GPS = HSUB + 0;     // g_p tile row length (hand fastest)
 
+template <bool USE_VP>
 __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* __restrict__ ws, const float* __restrict__ Kmat,
-                                                            int B, float img_res, SkinBwdIn gi) {
+                                                            int B, float img_res, SkinBwdIn gi, const float* __restrict__ vp) {
   extern __shared__ __align__(16) float smem[];
   float* Fs = smem;                   // [FS][HBF]
   float* As = Fs + FS * HBF;          // [HBF][AS]
@@ -344,7 +377,16 @@ __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* 
   }
   __syncthreads();
   float acc[HBF][3];
-  blend_gemm(c, Fs, v, acc);
+  if (USE_VP) {
+#pragma unroll
+    for (int h = 0; h < HBF; ++h) {
+      const int b = min(b0 + h, B - 1);
+      const float* src = vp + (size_t)b * (3 * VP) + v;
+      acc[h][0] = __ldg(src); acc[h][1] = __ldg(src + VP); acc[h][2] = __ldg(src + 2 * VP);
+    }
+  } else {
+    blend_gemm(c, Fs, v, acc);
+  }
   float w[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) w[j] = __ldg(c.Wt + j * VP + v);
@@ -775,7 +817,7 @@ using namespace hb;
 
 extern "C" size_t hb_mano_workspace_bytes(int B, int backward) {
   if (B <= 0) return 0;
-  return sizeof(float) * (backward ? ws_bwd_end(B) : ws_fwd_end(B));
+  return sizeof(float) * ws_tc_end(B, backward);
 }
 
 static int check_common(const hb_mano* h, const float* pose, const float* betas, const float* cam, const float* K, int B,
@@ -785,6 +827,14 @@ static int check_common(const hb_mano* h, const float* pose, const float* betas,
   if (wbytes < hb_mano_workspace_bytes(B, backward)) { set_error("hb_mano_head: workspace too small (%zu < %zu)", wbytes, hb_mano_workspace_bytes(B, backward)); return HB_E_WORKSPACE; }
   if (!aligned8(workspace) || (reinterpret_cast<uintptr_t>(workspace) & 15u)) { set_error("hb_mano_head: workspace must be 16-byte aligned"); return HB_E_ALIGN; }
   return 0;
+}
+
+static bool use_tc() {
+  if (g_mano_tc < 0) {
+    const char* e = getenv("HB_MANO_TC");
+    g_mano_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_mano_tc == 1;
 }
 
 static const size_t kSkinFwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + HBF * XS);
@@ -802,19 +852,26 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is
   if ((vertices && !aligned8(vertices)) || (v3d_cam && !aligned8(v3d_cam))) { set_error("hb_mano_head_fwd: vertex outputs must be 8-byte aligned"); return HB_E_ALIGN; }
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
-  PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s};
+  const bool tc = use_tc();
+  float* fh = tc ? ws + ws_tc_base(B, 0) : nullptr;
+  float* fl = tc ? fh + ws_tc_F(B) : nullptr;
+  float* vpo = tc ? fl + ws_tc_F(B) : nullptr;
+  PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
   mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, joints3d, j3d_cam, j2d_norm, cam_t);
   g_launches++;
   rc = check_launch("mano_pose_fwd_kernel");
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HB_CUDA(cudaFuncSetAttribute(mano_skin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinFwdSmem));
-    attr_set = true;
-  }
   SkinFwdOut o{vertices, v3d_cam, joints3d, j3d_cam, j2d_norm};
   dim3 grid((unsigned)ws_groups(B), NSLICE);
-  mano_skin_fwd_kernel<<<grid, VPB, kSkinFwdSmem, st>>>(h->c, ws, K, B, img_res, o);
+  if (tc) {
+    rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
+    if (rc) return rc;
+    HB_CUDA(cudaFuncSetAttribute(mano_skin_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinFwdSmem));
+    mano_skin_fwd_kernel<true><<<grid, VPB, kSkinFwdSmem, st>>>(h->c, ws, K, B, img_res, o, vpo);
+  } else {
+    HB_CUDA(cudaFuncSetAttribute(mano_skin_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinFwdSmem));
+    mano_skin_fwd_kernel<false><<<grid, VPB, kSkinFwdSmem, st>>>(h->c, ws, K, B, img_res, o, nullptr);
+  }
   g_launches++;
   return check_launch("mano_skin_fwd_kernel");
 }
@@ -832,19 +889,26 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is
   if (pre_rot && !pose_is_rotmat) { set_error("hb_mano_head_bwd: pre_rot needs rotation-matrix pose input"); return HB_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
-  PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s};
+  const bool tc = use_tc();
+  float* fh = tc ? ws + ws_tc_base(B, 1) : nullptr;
+  float* fl = tc ? fh + ws_tc_F(B) : nullptr;
+  float* vpo = tc ? fl + ws_tc_F(B) : nullptr;
+  PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
   mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, nullptr, nullptr, nullptr, nullptr);
   g_launches++;
   rc = check_launch("mano_pose_fwd_kernel");
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmem));
-    attr_set = true;
-  }
   SkinBwdIn gi{g_vertices, g_v3d_cam, g_joints3d, g_j3d_cam, g_j2d_norm};
   dim3 grid((unsigned)ws_groups(B), NSLICE);
-  mano_skin_bwd_kernel<<<grid, VPB, kSkinBwdSmem, st>>>(h->c, ws, K, B, img_res, gi);
+  if (tc) {
+    rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
+    if (rc) return rc;
+    HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmem));
+    mano_skin_bwd_kernel<true><<<grid, VPB, kSkinBwdSmem, st>>>(h->c, ws, K, B, img_res, gi, vpo);
+  } else {
+    HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmem));
+    mano_skin_bwd_kernel<false><<<grid, VPB, kSkinBwdSmem, st>>>(h->c, ws, K, B, img_res, gi, nullptr);
+  }
   g_launches++;
   rc = check_launch("mano_skin_bwd_kernel");
   if (rc) return rc;

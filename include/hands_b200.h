@@ -59,6 +59,10 @@ int hb_mano_create(const float* v_template_host, const float* shapedirs_host, co
                    const float* pose_mean_host, const int32_t* tip_ids_host, int device, hb_mano** out);
 int hb_mano_destroy(hb_mano* h);
 
+/* Blendshape contraction engine: 1 = tcgen05/TMEM tensor cores with 3xTF32 error compensation (default),
+ * 0 = register-tiled FFMA.  Environment HB_MANO_TC=0/1 sets the initial value.  Returns the previous setting. */
+int hb_mano_set_tensor_core(int on);
+
 /* Bytes of scratch the fwd / bwd calls need for a batch of B hands. */
 size_t hb_mano_workspace_bytes(int B, int backward);
 

@@ -104,6 +104,34 @@ def test_head_backward(heads, dev, B, is_rhand, edge, keys):
     assert (got[2].cpu()[small, 0] == 0).all()
 
 
+@pytest.mark.parametrize("B", [8, 300])
+def test_tensor_core_and_ffma_engines_agree(heads, dev, B):
+    """The blendshape contraction runs on tcgen05/TMEM (3xTF32) by default; the register-tiled FFMA engine stays
+    selectable.  Both must meet the oracle tolerances and agree with each other."""
+    from hands_b200 import _lib
+
+    lib = _lib.load()
+    rotmat, betas, cam, K = synthetic_head_inputs(B, seed=4242 + B, small_s_frac=0.1)
+    w = torch.randn(B, 778, 3, generator=torch.Generator().manual_seed(7)).to(dev)
+    ref64 = oracle_head(True, rotmat, betas, cam, K, torch.float64)
+    res = {}
+    prev = lib.hb_mano_set_tensor_core(1)
+    try:
+        for engine in (1, 0):
+            lib.hb_mano_set_tensor_core(engine)
+            r = rotmat.to(dev).requires_grad_(True)
+            bb = betas.to(dev).requires_grad_(True)
+            o = heads[True](r, bb, cam.to(dev), K.to(dev))
+            gr, gb = torch.autograd.grad((o["v3d.cam.r"] * w).sum() + o["j2d.norm.r"].sum(), (r, bb))
+            assert rel(o["vertices.r"], ref64["vertices"]) <= 1e-5, engine
+            assert rel(o["joints3d.r"], ref64["joints3d"]) <= 1e-5, engine
+            res[engine] = (o["vertices.r"].detach(), gr, gb)
+    finally:
+        lib.hb_mano_set_tensor_core(prev if prev >= 0 else 1)
+    assert rel(res[1][0], res[0][0].cpu()) <= 2e-6
+    assert rel(res[1][1], res[0][1].cpu()) <= 1e-5 and rel(res[1][2], res[0][2].cpu()) <= 1e-5
+
+
 def test_mano_layer_axis_angle_and_transl(dev):
     from hands_b200.common.body_models import build_mano_aa
 
