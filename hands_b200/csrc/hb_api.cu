@@ -68,9 +68,10 @@ extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, c
   const size_t nPk = (size_t)NP * 3 * VP, nPt = (size_t)3 * VP * FS, nVt = (size_t)3 * VP, nWt = (size_t)NJ * VP, nWv = (size_t)VP * NJ;
   const size_t nJt = NJ * 3, nJsd = NJ * 3 * NB, nPm = 48;
   const size_t nB = (size_t)10 * 19 * 240 * 8;   // tensor-core operand slabs
+  const size_t nPs = (size_t)300 * 160 * 8;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += (n + 3) / 4 * 4; return o; };  // keep 16-byte alignment
-  const size_t oPk = take(nPk), oPt = take(nPt), oVt = take(nVt), oWt = take(nWt), oWv = take(nWv), oJt = take(nJt), oJsd = take(nJsd), oPm = take(nPm), oBh = take(nB), oBl = take(nB);
+  const size_t oPk = take(nPk), oPt = take(nPt), oVt = take(nVt), oWt = take(nWt), oWv = take(nWv), oJt = take(nJt), oJsd = take(nJsd), oPm = take(nPm), oBh = take(nB), oBl = take(nB), oPh = take(nPs), oPl = take(nPs);
   std::vector<float> hostbuf(off, 0.0f);
   float* Pk = hostbuf.data() + oPk; float* Pt = hostbuf.data() + oPt; float* Vt = hostbuf.data() + oVt;
   float* Wt = hostbuf.data() + oWt; float* Wv = hostbuf.data() + oWv; float* Jt = hostbuf.data() + oJt;
@@ -114,6 +115,19 @@ extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, c
             const size_t o = ((size_t)tile * 19 + ks) * 1920 + (size_t)(kk >> 2) * 960 + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
             Bh[o] = hi; Bl[o] = lo;
           }
+    // backward reduction operand: rows = features p (160, zero above 144), K = c' (2400), slabs [k-step][k-half][row-group][row][4]
+    float* Ph = hostbuf.data() + oPh;
+    float* Pl = hostbuf.data() + oPl;
+    for (int ks = 0; ks < 300; ++ks)
+      for (int pidx = 0; pidx < 160; ++pidx)
+        for (int kk = 0; kk < 8; ++kk) {
+          const int cp = ks * 8 + kk;
+          const int k = cp / VP, v = cp % VP;
+          const float val = (pidx < NP && v < NV) ? Pk[((size_t)pidx * 3 + k) * VP + v] : 0.0f;
+          const float hi = tf32_round(val), lo = tf32_round(val - hi);
+          const size_t o = (size_t)ks * 1280 + (size_t)(kk >> 2) * 640 + (pidx >> 3) * 32 + (pidx & 7) * 4 + (kk & 3);
+          Ph[o] = hi; Pl[o] = lo;
+        }
   }
 
   int prev = -1;
@@ -129,7 +143,7 @@ extern "C" int hb_mano_create(const float* v_template, const float* shapedirs, c
     return (int)e;
   }
   const float* d = (const float*)blob;
-  c.Pk = d + oPk; c.Pt = d + oPt; c.Vt = d + oVt; c.Wt = d + oWt; c.Wv = d + oWv; c.Jt = d + oJt; c.Jsd = d + oJsd; c.pose_mean = d + oPm; c.Bhi = d + oBh; c.Blo = d + oBl;
+  c.Pk = d + oPk; c.Pt = d + oPt; c.Vt = d + oVt; c.Wt = d + oWt; c.Wv = d + oWv; c.Jt = d + oJt; c.Jsd = d + oJsd; c.pose_mean = d + oPm; c.Bhi = d + oBh; c.Blo = d + oBl; c.Ph = d + oPh; c.Pl = d + oPl;
   hb_mano* hm = new hb_mano;
   hm->c = c; hm->device = device; hm->blob = blob;
   *out = hm;

@@ -34,6 +34,8 @@ struct ManoConst {
   const float* pose_mean;  // [48]
   const float* Bhi;   // [10 tiles][19 k-steps][240 x 8] TF32 high parts of the stacked basis, UMMA slab order (mano_tc.cu)
   const float* Blo;   // same, low parts
+  const float* Ph;    // [300 k-steps][160 x 8] TF32 high parts of the basis for the backward reduction over vertex coordinates
+  const float* Pl;    // same, low parts
   int parents[NJ];
   int level[NJ];       // depth of each joint in the kinematic tree (root = 0)
   int child[NJ][5];    // child joints, -1 padded
@@ -64,6 +66,7 @@ __host__ __device__ inline float tf32_round(float x) {
 
 size_t tc_smem_bytes();
 int launch_blend_tc(const float* Fhi, const float* Flo, const float* Bhi, const float* Blo, const float* vt, int B, float* vp, cudaStream_t st);
+int launch_gfeat_tc(const float* gvh, const float* gvl, const float* Ph, const float* Pl, int B, float* gF, cudaStream_t st);
 extern int g_mano_tc;   // 1: blendshape contraction on tcgen05 (mano_tc.cu); 0: register-tiled FFMA
 
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }

@@ -34,7 +34,12 @@ __host__ __device__ inline size_t ws_bwd_end(int B) { return ws_gO(B) + (size_t)
 __host__ __device__ inline size_t ws_g128(int B) { return (size_t)(B + 127) / 128; }
 __host__ __device__ inline size_t ws_tc_base(int B, int backward) { return backward ? ws_bwd_end(B) : ws_fwd_end(B); }
 __host__ __device__ inline size_t ws_tc_F(int B) { return ws_g128(B) * 19 * 1024; }
-__host__ __device__ inline size_t ws_tc_end(int B, int backward) { return ws_tc_base(B, backward) + 2 * ws_tc_F(B) + ws_g128(B) * 128 * 2400; }
+__host__ __device__ inline size_t ws_tc_vp(int B) { return ws_g128(B) * 128 * 2400; }
+// backward only: dL/dv_posed slabs hi/lo [G128][300][1024] and the reduced feature gradient [G128*128][160]
+__host__ __device__ inline size_t ws_tc_gv(int B) { return ws_g128(B) * 300 * 1024; }
+__host__ __device__ inline size_t ws_tc_end(int B, int backward) {
+  return ws_tc_base(B, backward) + 2 * ws_tc_F(B) + ws_tc_vp(B) + (backward ? 2 * ws_tc_gv(B) + ws_g128(B) * 128 * 160 : 0);
+}
 
 // -------------------------------------------------------------------------------------------
 // per-(hand, joint) forward state
@@ -353,15 +358,18 @@ constexpr int GPS = HSUB + 0;     // g_p tile row length (hand fastest)
 
 template <bool USE_VP>
 __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* __restrict__ ws, const float* __restrict__ Kmat,
-                                                            int B, float img_res, SkinBwdIn gi, const float* __restrict__ vp) {
+                                                            int B, float img_res, SkinBwdIn gi, const float* __restrict__ vp,
+                                                            float* __restrict__ gvh, float* __restrict__ gvl) {
   extern __shared__ __align__(16) float smem[];
-  float* Fs = smem;                   // [FS][HBF]
-  float* As = Fs + FS * HBF;          // [HBF][AS]
-  float* Os = As + HBF * AS;          // [HBF][8]
-  float* Vs = Os + HBF * 8;           // [HSUB][XS]   v_posed
-  float* Gv = Vs + HSUB * XS;         // [HSUB][XS]   dL/dvertex
-  float* Gp = Gv + HSUB * XS;         // [VPB*3][HSUB] dL/dv_posed, hand fastest
-  float* Og = Gp + VPB * 3 * HSUB;    // [HSUB][8]    per-hand sums of g_vertices / g_v3d (+ tip joints)
+  // (in tensor-core mode the feature tile Fs and the dL/dv_posed tile Gp are not needed: the contraction and its
+  //  transpose run in mano_tc.cu)
+  float* Fs = smem;                                    // [FS][HBF]
+  float* As = Fs + (USE_VP ? 0 : FS * HBF);            // [HBF][AS]
+  float* Os = As + HBF * AS;                           // [HBF][8]
+  float* Vs = Os + HBF * 8;                            // [HSUB][XS]   v_posed
+  float* Gv = Vs + HSUB * XS;                          // [HSUB][XS]   dL/dvertex
+  float* Gp = Gv + HSUB * XS;                          // [VPB*3][HSUB] dL/dv_posed, hand fastest
+  float* Og = Gp + (USE_VP ? 0 : VPB * 3 * HSUB);      // [HSUB][8]    per-hand sums of g_vertices / g_v3d (+ tip joints)
   const int tid = threadIdx.x;
   const int g = blockIdx.x, slice = blockIdx.y;
   const int v = slice * VPB + tid;
@@ -371,22 +379,13 @@ __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* 
     const float4* srcF = reinterpret_cast<const float4*>(ws + ws_F(B) + (size_t)g * FS * HBF);
     const float4* srcA = reinterpret_cast<const float4*>(ws + ws_A(B) + (size_t)g * HBF * AS);
     const float4* srcO = reinterpret_cast<const float4*>(ws + ws_OFF(B) + (size_t)g * HBF * 8);
-    for (int idx = tid; idx < FS * HBF / 4; idx += VPB) reinterpret_cast<float4*>(Fs)[idx] = srcF[idx];
+    if (!USE_VP) for (int idx = tid; idx < FS * HBF / 4; idx += VPB) reinterpret_cast<float4*>(Fs)[idx] = srcF[idx];
     for (int idx = tid; idx < HBF * AS / 4; idx += VPB) reinterpret_cast<float4*>(As)[idx] = srcA[idx];
     for (int idx = tid; idx < HBF * 8 / 4; idx += VPB) reinterpret_cast<float4*>(Os)[idx] = srcO[idx];
   }
   __syncthreads();
-  float acc[HBF][3];
-  if (USE_VP) {
-#pragma unroll
-    for (int h = 0; h < HBF; ++h) {
-      const int b = min(b0 + h, B - 1);
-      const float* src = vp + (size_t)b * (3 * VP) + v;
-      acc[h][0] = __ldg(src); acc[h][1] = __ldg(src + VP); acc[h][2] = __ldg(src + 2 * VP);
-    }
-  } else {
-    blend_gemm(c, Fs, v, acc);
-  }
+  float acc[USE_VP ? 1 : HBF][3];
+  if (!USE_VP) blend_gemm(c, Fs, v, reinterpret_cast<float (&)[HBF][3]>(acc));
   float w[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) w[j] = __ldg(c.Wt + j * VP + v);
@@ -399,9 +398,16 @@ __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* 
     if (tid < HSUB * 8) Og[tid] = 0.f;
 #pragma unroll
     for (int hh = 0; hh < HSUB; ++hh) {
-      Vs[hh * XS + 3 * tid + 0] = acc[sub * HSUB + hh][0];
-      Vs[hh * XS + 3 * tid + 1] = acc[sub * HSUB + hh][1];
-      Vs[hh * XS + 3 * tid + 2] = acc[sub * HSUB + hh][2];
+      if (USE_VP) {
+        // v_posed from the tensor-core kernel: [hand][k][800], coalesced over vertices
+        const int b = min(b0 + sub * HSUB + hh, B - 1);
+        const float* src = vp + (size_t)b * (3 * VP) + v;
+        Vs[hh * XS + 3 * tid + 0] = __ldg(src); Vs[hh * XS + 3 * tid + 1] = __ldg(src + VP); Vs[hh * XS + 3 * tid + 2] = __ldg(src + 2 * VP);
+      } else {
+        Vs[hh * XS + 3 * tid + 0] = acc[USE_VP ? 0 : sub * HSUB + hh][0];
+        Vs[hh * XS + 3 * tid + 1] = acc[USE_VP ? 0 : sub * HSUB + hh][1];
+        Vs[hh * XS + 3 * tid + 2] = acc[USE_VP ? 0 : sub * HSUB + hh][2];
+      }
     }
     __syncthreads();
     // ---- phase L: per vertex, per hand: T_v, upstream vertex gradient, g_p = R_v^T gV
@@ -458,7 +464,21 @@ __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* 
         gp[2] = T[2] * gv[0] + T[6] * gv[1] + T[10] * gv[2];
       }
       Gv[hh * XS + 3 * tid + 0] = gv[0]; Gv[hh * XS + 3 * tid + 1] = gv[1]; Gv[hh * XS + 3 * tid + 2] = gv[2];
-      Gp[(3 * tid + 0) * GPS + hh] = gp[0]; Gp[(3 * tid + 1) * GPS + hh] = gp[1]; Gp[(3 * tid + 2) * GPS + hh] = gp[2];
+      if (USE_VP) {
+        // dL/dv_posed goes to the tensor-core reduction (mano_gfeat_tc_kernel) as TF32 hi/lo UMMA slabs:
+        // [group128][k-step = c'/8][k-half][row-group][row][4], c' = k*800 + v
+        const int hl = b % 128;
+        const size_t gb = (size_t)(b / 128) * 300 * 1024 + (size_t)(hl >> 3) * 32 + (hl & 7) * 4;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int cp = k * VP + v;
+          const size_t o = gb + (size_t)(cp >> 3) * 1024 + ((cp >> 2) & 1) * 512 + (cp & 3);
+          const float hi = tf32_round(gp[k]);
+          gvh[o] = hi; gvl[o] = tf32_round(gp[k] - hi);
+        }
+      } else {
+        Gp[(3 * tid + 0) * GPS + hh] = gp[0]; Gp[(3 * tid + 1) * GPS + hh] = gp[1]; Gp[(3 * tid + 2) * GPS + hh] = gp[2];
+      }
       // per-hand sums -> Og (warp shuffle then one smem atomic per warp)
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -493,7 +513,7 @@ __global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* 
       for (int k = 0; k < 12; ++k) dst[k] = ga[k];
     }
     // ---- phase F: gF[h][p] = sum_{k,v} Pt[k][v][p] g_p[v][k][h]                    thread = p
-    if (tid < FS) {
+    if (!USE_VP && tid < FS) {
       float gf[HSUB];
 #pragma unroll
       for (int hh = 0; hh < HSUB; ++hh) gf[hh] = 0.f;
@@ -535,7 +555,8 @@ struct PoseBwdArgs {
   float* g_pose; float* g_betas; float* g_cam; float* g_transl; float* g_pre_rot;
 };
 
-__global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArgs a, const float* __restrict__ ws, PoseBwdArgs o) {
+__global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArgs a, const float* __restrict__ ws, PoseBwdArgs o,
+                                                            const float* __restrict__ gFt) {
   const int i = threadIdx.x & 15;
   const int braw = blockIdx.x * 8 + (threadIdx.x >> 4);
   const bool live = braw < a.B;
@@ -561,14 +582,28 @@ __global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArg
     for (int k = 0; k < 12; ++k) gA[k] += pa[k];
     const float* pf = ws + ws_gF(a.B) + row * FS;
     if (i > 0) {
+      if (!gFt) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) gFr[k] += pf[(i - 1) * 9 + k];
+        for (int k = 0; k < 9; ++k) gFr[k] += pf[(i - 1) * 9 + k];
+      }
     } else {
+      if (!gFt) {
 #pragma unroll
-      for (int l = 0; l < NB; ++l) gbeta[l] += pf[NPF + l];
+        for (int l = 0; l < NB; ++l) gbeta[l] += pf[NPF + l];
+      }
       const float* po = ws + ws_gO(a.B) + row * 8;
 #pragma unroll
       for (int k = 0; k < 6; ++k) gO[k] += po[k];
+    }
+  }
+  if (gFt) {   // feature gradient reduced over all vertices by the tensor-core kernel: [hand][160]
+    const float* pf = gFt + (size_t)b * 160;
+    if (i > 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) gFr[k] = __ldg(pf + (i - 1) * 9 + k);
+    } else {
+#pragma unroll
+      for (int l = 0; l < NB; ++l) gbeta[l] = __ldg(pf + NPF + l);
     }
   }
   // gradient arriving at this posed joint: joints3d = t + t1 ; j3d_cam = joints3d + cam_t ; j2d = proj(j3d_cam)
@@ -839,6 +874,7 @@ static bool use_tc() {
 
 static const size_t kSkinFwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + HBF * XS);
 static const size_t kSkinBwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + 2 * HSUB * XS + VPB * 3 * HSUB + HSUB * 8);
+static const size_t kSkinBwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + 2 * HSUB * XS + HSUB * 8);
 
 extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot, const float* betas,
                                 const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
@@ -893,6 +929,9 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is
   float* fh = tc ? ws + ws_tc_base(B, 1) : nullptr;
   float* fl = tc ? fh + ws_tc_F(B) : nullptr;
   float* vpo = tc ? fl + ws_tc_F(B) : nullptr;
+  float* gvh = tc ? vpo + ws_tc_vp(B) : nullptr;
+  float* gvl = tc ? gvh + ws_tc_gv(B) : nullptr;
+  float* gft = tc ? gvl + ws_tc_gv(B) : nullptr;
   PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
   mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, nullptr, nullptr, nullptr, nullptr);
   g_launches++;
@@ -903,17 +942,21 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is
   if (tc) {
     rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
     if (rc) return rc;
-    HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmem));
-    mano_skin_bwd_kernel<true><<<grid, VPB, kSkinBwdSmem, st>>>(h->c, ws, K, B, img_res, gi, vpo);
+    HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmemTc));
+    mano_skin_bwd_kernel<true><<<grid, VPB, kSkinBwdSmemTc, st>>>(h->c, ws, K, B, img_res, gi, vpo, gvh, gvl);
   } else {
     HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmem));
-    mano_skin_bwd_kernel<false><<<grid, VPB, kSkinBwdSmem, st>>>(h->c, ws, K, B, img_res, gi, nullptr);
+    mano_skin_bwd_kernel<false><<<grid, VPB, kSkinBwdSmem, st>>>(h->c, ws, K, B, img_res, gi, nullptr, nullptr, nullptr);
   }
   g_launches++;
   rc = check_launch("mano_skin_bwd_kernel");
   if (rc) return rc;
+  if (tc) {
+    rc = launch_gfeat_tc(gvh, gvl, h->c.Ph, h->c.Pl, B, gft, st);
+    if (rc) return rc;
+  }
   PoseBwdArgs o{g_joints3d, g_j3d_cam, g_j2d_norm, g_cam_t, g_pose, g_betas, g_cam, g_transl, g_pre_rot};
-  mano_pose_bwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, o);
+  mano_pose_bwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, o, gft);
   g_launches++;
   return check_launch("mano_pose_bwd_kernel");
 }

