@@ -523,7 +523,8 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
 
 constexpr int PCL_TS = 32;              // source tile side
 constexpr int PCL_CELLS = PCL_TS + 1;   // cells = floor(sample position) in [tile-1, tile+31]
-constexpr int PCL_K = 8;                // list capacity per cell
+constexpr int PCL_K = 4;                // list capacity per cell (longer lists take the scan fallback)
+constexpr int PCL_REG = 2048;           // region pixels staged in shared memory per (tile, crop)
 
 // Transposed grid_sample, gather form.  One CTA per (image, 32x32 source tile); for each crop of the image:
 //   1. the tile's pre-image under the inverse homography bounds a region of the intermediate grid;
@@ -535,8 +536,11 @@ constexpr int PCL_K = 8;                // list capacity per cell
 template <int C>
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R, float* __restrict__ g_img) {
-  __shared__ int cnt[PCL_CELLS * PCL_CELLS];
-  __shared__ int lst[PCL_CELLS * PCL_CELLS * PCL_K];
+  extern __shared__ __align__(16) uint8_t img_sm[];
+  float4* ent_g = reinterpret_cast<float4*>(img_sm);                                   // [PCL_REG] staged region: gradient ...
+  float2* ent_p = reinterpret_cast<float2*>(img_sm + PCL_REG * 16);                    // [PCL_REG] ... and sample position
+  int* cnt = reinterpret_cast<int*>(img_sm + PCL_REG * 24);                            // [cells]
+  unsigned short* lst = reinterpret_cast<unsigned short*>(img_sm + PCL_REG * 24 + PCL_CELLS * PCL_CELLS * 4);  // [cells][K] region-local indices
   __shared__ int overflow;
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
@@ -595,15 +599,26 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     {
       const float inv_rw = 1.0f / (float)rw;
       const float cx_lo = (float)(tx0 - 1), cy_lo = (float)(ty0 - 1);
-      for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
-        const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
-        const int gidx = (rj0 + rr) * s + (ri0 + cc);
-        const float2 p = __ldg(POS + gidx);
-        const float fx = floorf(p.x) - cx_lo, fy = floorf(p.y) - cy_lo;
-        if (fx >= 0.0f && fx < (float)PCL_CELLS && fy >= 0.0f && fy < (float)PCL_CELLS) {
-          const int cell = (int)fy * PCL_CELLS + (int)fx;
-          const int slot = atomicAdd(&cnt[cell], 1);
-          if (slot < PCL_K) lst[cell * PCL_K + slot] = gidx; else overflow = 1;
+      if (rw * rh > PCL_REG) {
+        if (threadIdx.x == 0) overflow = 1;   // region too large to stage (extreme foreshortening): scan fallback
+      } else {
+        // stage the region with cp.async (all of a thread's loads in flight at once, no register staging) ...
+        for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
+          const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
+          const int gidx = (rj0 + rr) * s + (ri0 + cc);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(ent_p + idx)), "l"(POS + gidx) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ent_g + idx)), "l"(G + gidx) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        // ... then bin this thread's own entries (it waited for its own copies; no barrier needed yet)
+        for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
+          const float2 p = ent_p[idx];
+          const float fx = floorf(p.x) - cx_lo, fy = floorf(p.y) - cy_lo;
+          if (fx >= 0.0f && fx < (float)PCL_CELLS && fy >= 0.0f && fy < (float)PCL_CELLS) {
+            const int cell = (int)fy * PCL_CELLS + (int)fx;
+            const int slot = atomicAdd(&cnt[cell], 1);
+            if (slot < PCL_K) lst[cell * PCL_K + slot] = (unsigned short)idx; else overflow = 1;
+          }
         }
       }
     }
@@ -614,9 +629,9 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     if (!slow) {
       for (int cell = threadIdx.x; cell < PCL_CELLS * PCL_CELLS; cell += PCL_THREADS) {
         const int n = cnt[cell];
-        int* l = lst + cell * PCL_K;
+        unsigned short* l = lst + cell * PCL_K;
         for (int a = 1; a < n; ++a) {
-          const int v = l[a];
+          const unsigned short v = l[a];
           int b = a - 1;
           while (b >= 0 && l[b] > v) { l[b + 1] = l[b]; --b; }
           l[b + 1] = v;
@@ -640,8 +655,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
             const int n = cnt[cell];
             for (int e = 0; e < n; ++e) {
               const int cur = lst[cell * PCL_K + e];
-              const float2 p = __ldg(POS + cur);
-              const float4 g = __ldg(G + cur);
+              const float2 p = ent_p[cur];
+              const float4 g = ent_g[cur];
               const float w = (1.0f - fabsf(p.x - fsx)) * (1.0f - fabsf(p.y - fsy));
               const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -738,6 +753,8 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
   HB_CUDA(cudaFuncSetAttribute(pcl_bwd_mid_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
+  const size_t smem_img = (size_t)PCL_REG * 24 + (size_t)PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K);
+  HB_CUDA(cudaFuncSetAttribute(pcl_bwd_img_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int im0 = ch * chunk_imgs;
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
@@ -747,7 +764,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     rc = check_launch("pcl_bwd_mid_kernel");
     if (rc) return rc;
     dim3 g2(tiles, nim);
-    pcl_bwd_img_kernel<C><<<g2, PCL_THREADS, 0, st>>>(params, ws, im0, crops_per_img, R, g_img);
+    pcl_bwd_img_kernel<C><<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img);
     g_launches++;
     rc = check_launch("pcl_bwd_img_kernel");
     if (rc) return rc;
