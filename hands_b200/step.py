@@ -33,7 +33,8 @@ class GeometryStep:
         S, R, dev = self.S, self.R, self.dev
         f32 = dict(dtype=torch.float32, device=dev)
         self.s_pcl = torch.cuda.Stream(device=dev)
-        self.s_mano = torch.cuda.Stream(device=dev)
+        # equal priority measured best on B200 (16.60 ms vs 16.75 ms with the MANO stream at -1)
+        self.s_mano = torch.cuda.Stream(device=dev, priority=int(os.environ.get("HB_MANO_STREAM_PRIORITY", "0")))
         self.ev_setup = torch.cuda.Event()
         self.ev_start = torch.cuda.Event()
         self.ev_pcl_done = torch.cuda.Event()
