@@ -13,6 +13,7 @@
 // The fp32 operation order (which products are fused) follows torch's CPU kernels exactly; it was pinned
 // by bit-comparing a numpy emulation against torch 2.11 single-threaded ("PCL exactness").
 #include <climits>
+#include <cstdlib>
 #include "hb_common.cuh"
 #include "tma.cuh"
 
@@ -114,8 +115,10 @@ __device__ __forceinline__ int fast_div(int idx, int s, float inv_s) {
 //            registers while consecutive output rows share them (up-sampling), stores are coalesced rows.
 template <int C>
 __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __restrict__ img, const float* __restrict__ params,
-                                                              int crops_per_img, int R, float* __restrict__ out, int max_rows) {
-  extern __shared__ __align__(16) float4 mid4[];  // [max_rows][s] pixels, channels in .x .y .z .w
+                                                              int crops_per_img, int R, float* __restrict__ out, int max_rows, int smem_bytes, int tma_ok) {
+  extern __shared__ __align__(16) float4 mid4[];  // [nrows][s] pixels, channels in .x .y .z .w; then the staged source tile
+  __shared__ int reg[5];                          // staged source region: x0, y0, ncols, nrows, staged?
+  __shared__ uint64_t src_bar;
   const int q = blockIdx.y;
   const Crop c = load_crop(params + (size_t)q * PF);
   const int s = c.s;
@@ -135,10 +138,61 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
   if (staged) {
     const int n = nrows * s;
     const float inv_s = 1.0f / (float)s;
+    float* stile = reinterpret_cast<float*>(mid4 + n);   // source tile [C][rows][cols], cols a multiple of 4
+    // ---- TMA-staged source tile: the band's sample positions are the image of a rectangle of the intermediate grid
+    //      under a homography, a convex quad whose corner box (+ margin) bounds every bilinear tap.  Warp 0 finds the
+    //      box and issues one bulk copy per (channel, row); the copies land while all warps do the position math.
+    //      (Measured on B200: 4.78 ms vs 4.53 ms for gathering straight through L1 -- the kernel is issue-bound, so the
+    //      staging instructions cost more than the L1 misses they remove; HB_PCL_TMA=0 selects the direct gather.)
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      float cx = 0.f, cy = 0.f;
+      if (lane < 4) sample_pos(c, (lane >> 1) ? jhi : jlo, (lane & 1) ? s - 1 : 0, Rf, rcpR, cx, cy);
+      float xmn = lane < 4 ? cx : 3.0e38f, xmx = lane < 4 ? cx : -3.0e38f, ymn = lane < 4 ? cy : 3.0e38f, ymx = lane < 4 ? cy : -3.0e38f;
+#pragma unroll
+      for (int m = 1; m < 4; m <<= 1) {
+        xmn = fminf(xmn, __shfl_xor_sync(0xffffffffu, xmn, m)); xmx = fmaxf(xmx, __shfl_xor_sync(0xffffffffu, xmx, m));
+        ymn = fminf(ymn, __shfl_xor_sync(0xffffffffu, ymn, m)); ymx = fmaxf(ymx, __shfl_xor_sync(0xffffffffu, ymx, m));
+      }
+      xmn = __shfl_sync(0xffffffffu, xmn, 0); xmx = __shfl_sync(0xffffffffu, xmx, 0);
+      ymn = __shfl_sync(0xffffffffu, ymn, 0); ymx = __shfl_sync(0xffffffffu, ymx, 0);
+      int use = 0, bx0 = 0, by0 = 0, ncols = 0, nr = 0;
+      if (tma_ok && xmn == xmn && xmx == xmx && ymn == ymn && ymx == ymx && xmx > -2.0f && ymx > -2.0f && xmn < Rf + 1.0f && ymn < Rf + 1.0f) {
+        const int xl = max(0, (int)floorf(fmaxf(xmn, -4.0f)) - 1), xh = min(R - 1, (int)floorf(fminf(xmx, Rf + 4.0f)) + 2);
+        const int yl = max(0, (int)floorf(fmaxf(ymn, -4.0f)) - 1), yh = min(R - 1, (int)floorf(fminf(ymx, Rf + 4.0f)) + 2);
+        bx0 = xl & ~3;
+        ncols = min(R - bx0, (xh - bx0 + 4) & ~3);
+        by0 = yl;
+        nr = yh - yl + 1;
+        use = nr > 0 && ncols > 0 && (size_t)n * 16 + (size_t)C * nr * ncols * 4 <= (size_t)smem_bytes;
+      }
+      if (lane == 0) {
+        reg[0] = bx0; reg[1] = by0; reg[2] = ncols; reg[3] = nr; reg[4] = use;
+        if (use) { mbar_init(&src_bar, 1); mbar_fence_init(); mbar_arrive_expect_tx(&src_bar, (uint32_t)(C * nr * ncols * 4)); }
+      }
+      __syncwarp();
+      if (use) {
+        for (int k = lane; k < C * nr; k += 32) {
+          const int ch = k / nr, r = k - ch * nr;
+          bulk_g2s(stile + (size_t)k * ncols, src + (size_t)ch * plane + (size_t)(by0 + r) * R + bx0, (uint32_t)(ncols * 4), &src_bar);
+        }
+      }
+    }
+    // pass 1: sample positions (kept in the tile itself) -- the bulk copies land meanwhile
     for (int idx = threadIdx.x; idx < n; idx += PCL_THREADS) {
       const int jr = fast_div(idx, s, inv_s), i = idx - jr * s;
       float ix, iy;
       sample_pos(c, jlo + jr, i, Rf, rcpR, ix, iy);
+      mid4[idx] = make_float4(ix, iy, 0.f, 0.f);
+    }
+    __syncthreads();   // region parameters and the barrier init are visible
+    const int rx0 = reg[0], ry0 = reg[1], rnc = reg[2], rnr = reg[3];
+    const bool tiled = reg[4] != 0;
+    if (tiled) mbar_wait(&src_bar, 0);
+    // pass 2: bilinear gather (from the staged tile; a tap outside it -- never expected -- falls back to global)
+    for (int idx = threadIdx.x; idx < n; idx += PCL_THREADS) {
+      const float4 pq = mid4[idx];
+      const float ix = pq.x, iy = pq.y;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (ix > -1.0f && ix < Rf && iy > -1.0f && iy < Rf) {
         const float fx = floorf(ix), fy = floorf(iy);
@@ -148,19 +202,39 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
         const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
         const bool xa = x0 >= 0, xb = x0 + 1 < R, ya = yy0 >= 0, yb = yy0 + 1 < R;
         const int o00 = yy0 * R + x0;
-        const float* pl = src;
+        // are the (in-image) taps x0..x0+1, yy0..yy0+1 inside the staged tile?
+        const int tx = x0 - rx0, ty = yy0 - ry0;
+        const bool in_tile = tiled && tx >= (xa ? 0 : -1) && tx + 1 < rnc + (xb ? 0 : 1) && ty >= (ya ? 0 : -1) && ty + 1 < rnr + (yb ? 0 : 1);
+        if (in_tile) {
+          const float* tl = stile + ty * rnc + tx;
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) {
-          const float nw = (xa && ya) ? __ldg(pl + o00) : 0.0f;
-          const float ne = (xb && ya) ? __ldg(pl + o00 + 1) : 0.0f;
-          const float sw = (xa && yb) ? __ldg(pl + o00 + R) : 0.0f;
-          const float se = (xb && yb) ? __ldg(pl + o00 + R + 1) : 0.0f;
-          float acc = __fmul_rn(nw, wnw);
-          acc = fmaf(ne, wne, acc);
-          acc = fmaf(sw, wsw, acc);
-          acc = fmaf(se, wse, acc);
-          v[ch] = acc;
-          pl += plane;
+          for (int ch = 0; ch < C; ++ch) {
+            const float nw = (xa && ya) ? tl[0] : 0.0f;
+            const float ne = (xb && ya) ? tl[1] : 0.0f;
+            const float sw = (xa && yb) ? tl[rnc] : 0.0f;
+            const float se = (xb && yb) ? tl[rnc + 1] : 0.0f;
+            float acc = __fmul_rn(nw, wnw);
+            acc = fmaf(ne, wne, acc);
+            acc = fmaf(sw, wsw, acc);
+            acc = fmaf(se, wse, acc);
+            v[ch] = acc;
+            tl += rnr * rnc;
+          }
+        } else {
+          const float* pl = src;
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            const float nw = (xa && ya) ? __ldg(pl + o00) : 0.0f;
+            const float ne = (xb && ya) ? __ldg(pl + o00 + 1) : 0.0f;
+            const float sw = (xa && yb) ? __ldg(pl + o00 + R) : 0.0f;
+            const float se = (xb && yb) ? __ldg(pl + o00 + R + 1) : 0.0f;
+            float acc = __fmul_rn(nw, wnw);
+            acc = fmaf(ne, wne, acc);
+            acc = fmaf(sw, wsw, acc);
+            acc = fmaf(se, wse, acc);
+            v[ch] = acc;
+            pl += plane;
+          }
         }
       }
       mid4[idx] = make_float4(v[0], v[1], v[2], v[3]);
@@ -696,11 +770,16 @@ using namespace hb;
 template <int C>
 static int launch_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int R, float* out, cudaStream_t st) {
   const int max_rows = PCL_TR + 2;
-  const size_t smem = sizeof(float4) * (size_t)max_rows * R;
+  size_t smem = sizeof(float4) * (size_t)max_rows * R;        // worst case of the intermediate tile (s == R)
   if (smem > 200 * 1024) { set_error("hb_pcl_fwd: img_res too large for the staged kernel"); return HB_E_UNSUPPORTED; }
+  if (smem < 72 * 1024) smem = 72 * 1024;                     // room for the TMA-staged source tile next to a typical tile
+  // bulk copies need 16-byte aligned row segments: R % 4 == 0 and a 16-byte aligned image
+  static int want_tma = -1;
+  if (want_tma < 0) { const char* e = getenv("HB_PCL_TMA"); want_tma = (e && e[0] == '0') ? 0 : 1; }
+  const int tma_ok = want_tma && (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
   HB_CUDA(cudaFuncSetAttribute(pcl_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((R + PCL_TR - 1) / PCL_TR, n_crops);
-  pcl_fwd_kernel<C><<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, max_rows);
+  pcl_fwd_kernel<C><<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, max_rows, (int)smem, tma_ok);
   g_launches++;
   return check_launch("pcl_fwd_kernel");
 }
