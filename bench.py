@@ -235,27 +235,50 @@ def run_ours(args, rank, world, local_rank):
     hands_per_step = S * HANDS_PER_SAMPLE * world
     value = hands_per_step * args.steps / elapsed
 
-    # ---- per-kernel-family timing (alone, same stream) for the roofline ---------------------------
+    # ---- per-kernel timing (each kernel alone on the current stream, CUDA events) for the roofline ------------
+    # One-chunk batch (1024 images = 2048 crops = the launch shape of the backward chunks in the timed step), so one
+    # call == one launch of the kernel in question.
     peak, peak_src = peaks()
-    fam = {}
+    fam, kern = {}, {}
     if rank == 0:
         n = step.n
         plane = 3 * IMG_RES * IMG_RES * 4
+        reps = max(5, args.steps)
         step.pcl_setup()
-        t_fwd = cuda_time(step.pcl_forward, max(3, args.steps), 2, dev)
-        t_bwd = cuda_time(step.pcl_backward, max(3, args.steps), 2, dev)
-        t_mf = cuda_time(lambda: step.mano_forward(0), max(3, args.steps), 2, dev)
-        t_mb = cuda_time(lambda: step.mano_backward(0), max(3, args.steps), 2, dev)
+        t_fwd = cuda_time(step.pcl_forward, reps, 2, dev)
+        t_bwd = cuda_time(step.pcl_backward, reps, 2, dev)
+        t_mf = cuda_time(lambda: step.mano_forward(0), reps, 2, dev)
+        t_mb = cuda_time(lambda: step.mano_backward(0), reps, 2, dev)
         b_fwd = n * (plane + 12.0 * step.mean_s2)
         b_bwd = n * plane + S * plane
         fam = {
-            "pcl_fwd_kernel": {"ms": t_fwd * 1e3, "alg_bytes": b_fwd, "gbs": b_fwd / t_fwd / 1e9, "frac": b_fwd / t_fwd / 1e9 / peak},
-            "pcl_bwd (mid+img kernels)": {"ms": t_bwd * 1e3, "alg_bytes": b_bwd, "gbs": b_bwd / t_bwd / 1e9, "frac": b_bwd / t_bwd / 1e9 / peak},
-            "mano_fwd (pose+skin)": {"ms": t_mf * 1e3, "alg_bytes": S * 20020.0, "gbs": S * 20020.0 / t_mf / 1e9, "frac": S * 20020.0 / t_mf / 1e9 / peak,
-                                     "hands_per_s": S / t_mf},
-            "mano_bwd (pose+skin+pose)": {"ms": t_mb * 1e3, "alg_bytes": S * 11048.0, "gbs": S * 11048.0 / t_mb / 1e9, "frac": S * 11048.0 / t_mb / 1e9 / peak,
-                                          "hands_per_s": S / t_mb},
+            "pcl_fwd": {"ms": t_fwd * 1e3, "alg_bytes": b_fwd, "gbs": b_fwd / t_fwd / 1e9, "frac": b_fwd / t_fwd / 1e9 / peak},
+            "pcl_bwd (scan + mid + img kernels, all chunks)": {"ms": t_bwd * 1e3, "alg_bytes": b_bwd, "gbs": b_bwd / t_bwd / 1e9, "frac": b_bwd / t_bwd / 1e9 / peak},
+            "mano_fwd (pose + blend_tc + skin)": {"ms": t_mf * 1e3, "alg_bytes": S * 20020.0, "gbs": S * 20020.0 / t_mf / 1e9, "frac": S * 20020.0 / t_mf / 1e9 / peak,
+                                                  "hands_per_s": S / t_mf},
+            "mano_bwd (pose + blend_tc + skin + gfeat_tc + pose)": {"ms": t_mb * 1e3, "alg_bytes": S * 11048.0, "gbs": S * 11048.0 / t_mb / 1e9,
+                                                                    "frac": S * 11048.0 / t_mb / 1e9 / peak, "hands_per_s": S / t_mb},
         }
+        Sk = min(S, 1024)
+        ks = step if S == Sk else GeometryStep(Sk, dev, img_res=IMG_RES, seed=7)
+        ks.pcl_setup()
+        ks.pcl_forward()
+        ks.pcl_backward()
+        tk_fwd = cuda_time(ks.pcl_forward, reps, 2, dev)
+        tk_mid = cuda_time(lambda: ks.pcl_backward_stage(1), reps, 2, dev)
+        tk_img = cuda_time(lambda: ks.pcl_backward_stage(2), reps, 2, dev)
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
+                traffic = json.load(fh)
+        except Exception:
+            pass
+        ab = {"pcl_fwd_kernel": ks.n * (plane + 12.0 * ks.mean_s2), "pcl_bwd_mid_kernel": ks.n * plane, "pcl_bwd_img_kernel": Sk * plane}
+        tt = {"pcl_fwd_kernel": tk_fwd, "pcl_bwd_mid_kernel": tk_mid, "pcl_bwd_img_kernel": tk_img}
+        for name in ab:
+            kern[name] = {"us_per_launch": tt[name] * 1e6, "alg_bytes_per_launch": ab[name], "achieved": ab[name] / tt[name] / 1e9,
+                          "frac": ab[name] / tt[name] / 1e9 / peak, "traffic": traffic.get(name), "crops_per_launch": ks.n}
+        del ks
 
     # ---- e2e: host buffers, copies inside the timed region ---------------------------------------------
     e2e = None
@@ -264,7 +287,11 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    dom = max(("pcl_fwd_kernel", "pcl_bwd (mid+img kernels)"), key=lambda k: fam[k]["ms"])
+    # share of the step: forward launches once per step, the two backward kernels once per 1024-image chunk
+    chunks = max(1, (S + 1023) // 1024)
+    share = {"pcl_fwd_kernel": fam["pcl_fwd"]["ms"], "pcl_bwd_mid_kernel": kern["pcl_bwd_mid_kernel"]["us_per_launch"] * 1e-3 * chunks,
+             "pcl_bwd_img_kernel": kern["pcl_bwd_img_kernel"]["us_per_launch"] * 1e-3 * chunks}
+    dom = max(share, key=share.get)
     step_bytes = step.bytes_per_sample() * S
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -274,15 +301,18 @@ def run_ours(args, rank, world, local_rank):
                    "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
-                   "streams": "pcl || mano" if not args.no_overlap else "single"},
+                   "streams": "pcl || mano" if not args.no_overlap else "single",
+                   "mano_contractions": "tcgen05 3xTF32" if os.environ.get("HB_MANO_TC", "1") != "0" else "ffma"},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": e2e,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": fam[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": fam[dom]["frac"], "traffic": None,
-                     "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
+                     "traffic": kern[dom]["traffic"], "peak_source": peak_src,
+                     "note": "dominant kernel timed alone, one launch over %d crops; achieved = algorithmic bytes of that launch / CUDA-event time" % kern[dom]["crops_per_launch"],
+                     "step_share_ms": share,
                      "step": {"alg_bytes_per_sample": step.bytes_per_sample(), "achieved": value / world / HANDS_PER_SAMPLE * step.bytes_per_sample() / 1e9,
                               "frac": value / world / HANDS_PER_SAMPLE * step.bytes_per_sample() / 1e9 / peak},
-                     "families": fam},
+                     "kernels": kern, "families": fam},
     }
     if world == 1 and not args.no_cpu_baseline:
         hps, dt = time_cpu_reference(args.ref_samples, 2, 1)

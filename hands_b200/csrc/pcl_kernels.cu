@@ -817,16 +817,19 @@ extern "C" size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int
 }
 
 template <int C>
-static int launch_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int R, float* g_img, float* ws, size_t ws_bytes, cudaStream_t st) {
+static int launch_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int R, float* g_img, float* ws, size_t ws_bytes, int stages, cudaStream_t st) {
   const int n_imgs = n_crops / crops_per_img;
   const size_t fit = ws_bytes / pcl_ws_bytes_per_img(crops_per_img, R);
   const int chunk_imgs = (size_t)n_imgs < fit ? n_imgs : (int)fit;
   const int chunk_crops = chunk_imgs * crops_per_img;
   const int n_chunks = (n_imgs + chunk_imgs - 1) / chunk_imgs;
-  pcl_offsets_kernel<<<n_chunks, 1024, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops);
-  g_launches++;
-  int rc = check_launch("pcl_offsets_kernel");
-  if (rc) return rc;
+  int rc = 0;
+  if (stages & 1) {
+    pcl_offsets_kernel<<<n_chunks, 1024, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops);
+    g_launches++;
+    rc = check_launch("pcl_offsets_kernel");
+    if (rc) return rc;
+  }
   const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + 2 * PCL_NS + (size_t)PCL_NS * C * PCL_RB * R);
   // bulk copies need 16-byte aligned rows: R % 4 == 0 and a 16-byte aligned g_out
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
@@ -838,23 +841,27 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     const int im0 = ch * chunk_imgs;
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
     dim3 g1((R + PCL_JR - 1) / PCL_JR, nim * crops_per_img);
-    pcl_bwd_mid_kernel<C><<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
-    g_launches++;
-    rc = check_launch("pcl_bwd_mid_kernel");
-    if (rc) return rc;
+    if (stages & 1) {
+      pcl_bwd_mid_kernel<C><<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
+      g_launches++;
+      rc = check_launch("pcl_bwd_mid_kernel");
+      if (rc) return rc;
+    }
     dim3 g2(tiles, nim);
-    pcl_bwd_img_kernel<C><<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img);
-    g_launches++;
-    rc = check_launch("pcl_bwd_img_kernel");
-    if (rc) return rc;
+    if (stages & 2) {
+      pcl_bwd_img_kernel<C><<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img);
+      g_launches++;
+      rc = check_launch("pcl_bwd_img_kernel");
+      if (rc) return rc;
+    }
   }
   return 0;
 }
 
-extern "C" int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res, float* g_img,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int hb_pcl_bwd_stages(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res, float* g_img,
+                                 void* workspace, size_t workspace_bytes, int stages, void* stream) {
   if (n_crops < 0 || crops_per_img <= 0 || C <= 0 || C > 4 || img_res <= 0 || (n_crops > 0 && (!g_out || !params || !g_img || !workspace)) ||
-      n_crops % crops_per_img) {
+      n_crops % crops_per_img || (stages & 3) == 0) {
     set_error("hb_pcl_bwd: bad argument (1 <= C <= 4)"); return HB_E_ARG;
   }
   if (n_crops == 0) return 0;
@@ -863,9 +870,14 @@ extern "C" int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, 
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   switch (C) {
-    case 1: return launch_bwd<1>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
-    case 2: return launch_bwd<2>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
-    case 3: return launch_bwd<3>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
-    default: return launch_bwd<4>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, st);
+    case 1: return launch_bwd<1>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, stages, st);
+    case 2: return launch_bwd<2>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, stages, st);
+    case 3: return launch_bwd<3>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, stages, st);
+    default: return launch_bwd<4>(g_out, params, n_crops, crops_per_img, img_res, g_img, ws, workspace_bytes, stages, st);
   }
+}
+
+extern "C" int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res, float* g_img,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  return hb_pcl_bwd_stages(g_out, params, n_crops, crops_per_img, C, img_res, g_img, workspace, workspace_bytes, 3, stream);
 }

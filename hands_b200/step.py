@@ -96,6 +96,11 @@ class GeometryStep:
         _lib.check(self.lib.hb_pcl_bwd(_ptr(self.g_crops), _ptr(self.params), self.n, self.hps, 3, self.R, _ptr(self.g_img), _ptr(self.pcl_ws),
                                        self.pcl_ws_bytes, self._st()), "hb_pcl_bwd")
 
+    def pcl_backward_stage(self, stages):
+        """stages 1 = transposed resize, 2 = transposed gather (single-chunk batches only; used by bench.py's roofline leg)."""
+        _lib.check(self.lib.hb_pcl_bwd_stages(_ptr(self.g_crops), _ptr(self.params), self.n, self.hps, 3, self.R, _ptr(self.g_img), _ptr(self.pcl_ws),
+                                              self.pcl_ws_bytes, int(stages), self._st()), "hb_pcl_bwd_stages")
+
     def gather_pre_rot(self):
         # rot is (S*hps,3,3) interleaved [sample][side]; each hand side takes its strided view (one small copy kernel)
         for side, h in enumerate(self.hands):

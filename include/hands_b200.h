@@ -135,6 +135,12 @@ size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int C, int img
 int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res,
                float* g_img, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two stages of the backward separately (profiling / benchmarking): stages bit 0 = offset scan + transposed
+ * resize (g_out -> workspace), bit 1 = transposed gather (workspace -> g_img).  hb_pcl_bwd == stages 3.  Only
+ * meaningful stage by stage when the whole batch fits one chunk of the workspace. */
+int hb_pcl_bwd_stages(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res,
+                      float* g_img, void* workspace, size_t workspace_bytes, int stages, void* stream);
+
 /* ---- counters ---------------------------------------------------------------------------------
  * Number of kernels this library has launched since load (all threads). bench.py reports the delta. */
 uint64_t hb_launch_count(void);

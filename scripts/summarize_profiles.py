@@ -56,6 +56,7 @@ def kernels():
     idx = {h: i for i, h in enumerate(hdr)}
     stalls = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
     seen = set()
+    traffic = {}
     with open(os.path.join(OUT, f"kernels_{TAG}.txt"), "w") as fh:
         fh.write("# ncu --set full --clock-control none --import-source on (one capture per kernel; first instance of each shown)\n")
         for n, r in enumerate(rows[2:]):
@@ -63,6 +64,14 @@ def kernels():
             if name in seen:
                 continue
             seen.add(name)
+            try:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+                wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+                short = name.replace("void ", "").split("<")[0].split("(")[0].split("::")[-1]
+                traffic[short] = rd + wr
+            except Exception:
+                pass
             fh.write(f"\n== {name}\n")
             for m in METRICS:
                 if m in idx:
@@ -90,6 +99,9 @@ def kernels():
                 fh.write("   hottest source lines (share of warp instructions / of stall samples):\n")
                 for inst, samp, line, text in sorted(items, reverse=True)[:8]:
                     fh.write(f"     {100*inst/ti:5.1f}% {100*samp/ts:5.1f}%  L{line:<4d} {text[:100]}\n")
+    import json
+    with open(os.path.join(OUT, f"traffic_{TAG}.json"), "w") as fh:
+        json.dump(traffic, fh, indent=1)
 
 
 if __name__ == "__main__":
