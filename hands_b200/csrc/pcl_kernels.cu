@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   int* cnt = reinterpret_cast<int*>(img_sm + PCL_REG * 24);                            // [cells]
   unsigned short* lst = reinterpret_cast<unsigned short*>(img_sm + PCL_REG * 24 + PCL_CELLS * PCL_CELLS * 4);  // [cells][K] region-local indices
   __shared__ int overflow;
+  __shared__ int box[4];
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
   const int im = img_base + blockIdx.y;
@@ -632,43 +633,49 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     if (__float_as_int(__ldg(rec + 22)) > tx0 + PCL_TS || __float_as_int(__ldg(rec + 23)) < tx0 - 1 ||
         __float_as_int(__ldg(rec + 24)) > ty0 + PCL_TS || __float_as_int(__ldg(rec + 25)) < ty0 - 1) continue;
     const int s = __float_as_int(__ldg(rec + 18));
-    float Pi[9];
-#pragma unroll
-    for (int e = 0; e < 9; ++e) Pi[e] = __ldg(rec + 9 + e);
     const float* base = ws + __float_as_int(__ldg(rec + 21));
     const float4* G = reinterpret_cast<const float4*>(base);
     const float2* POS = reinterpret_cast<const float2*>(base + 4 * (size_t)s * s);
-    const float sm1 = (float)(s - 1);
-    // 1. region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
-    //    sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5)
-    float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
-    bool bad = false;
+    __syncthreads();  // previous crop's readers are done with cnt/lst/ent and the region box
+    if (threadIdx.x < 32) {
+      // 1. (warp 0) region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
+      //    sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5); the pre-image
+      //    of that box under the inverse homography is a convex quad, bounded by the box of its four corners
+      float Pi[9];
 #pragma unroll
-    for (int cy = 0; cy < 2; ++cy)
+      for (int e = 0; e < 9; ++e) Pi[e] = __ldg(rec + 9 + e);
+      const float sm1 = (float)(s - 1);
+      float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
+      bool bad = false;
 #pragma unroll
-      for (int cx = 0; cx < 2; ++cx) {
-        const float gx = (float)tx0 - 0.5f + 33.0f * cx, gy = (float)ty0 - 0.5f + 33.0f * cy;
-        const float U = Pi[0] * gx + Pi[1] * gy + Pi[2];
-        const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
-        const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
-        if (Wd > 1e-12f) {
-          const float iw = __frcp_rn(Wd);
-          const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
-          ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
-        } else bad = true;
+      for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          const float gx = (float)tx0 - 0.5f + 33.0f * cx, gy = (float)ty0 - 0.5f + 33.0f * cy;
+          const float U = Pi[0] * gx + Pi[1] * gy + Pi[2];
+          const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
+          const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
+          if (Wd > 1e-12f) {
+            const float iw = __frcp_rn(Wd);
+            const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
+            ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
+          } else bad = true;
+        }
+      if (threadIdx.x == 0) {
+        if (bad) { box[0] = 0; box[1] = s - 1; box[2] = 0; box[3] = s - 1; }
+        else {
+          box[0] = max(0, (int)floorf(ilo - 0.25f)); box[1] = min(s - 1, (int)ceilf(ihi + 0.25f));
+          box[2] = max(0, (int)floorf(jlo - 0.25f)); box[3] = min(s - 1, (int)ceilf(jhi + 0.25f));
+        }
+        overflow = 0;
       }
-    int ri0, ri1, rj0, rj1;
-    if (bad) { ri0 = 0; ri1 = s - 1; rj0 = 0; rj1 = s - 1; }
-    else {
-      ri0 = max(0, (int)floorf(ilo - 0.25f)); ri1 = min(s - 1, (int)ceilf(ihi + 0.25f));
-      rj0 = max(0, (int)floorf(jlo - 0.25f)); rj1 = min(s - 1, (int)ceilf(jhi + 0.25f));
+    } else {
+      for (int idx = threadIdx.x - 32; idx < PCL_CELLS * PCL_CELLS; idx += PCL_THREADS - 32) cnt[idx] = 0;
     }
-    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (same decision in every thread)
-    const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
-    __syncthreads();  // previous crop's readers are done with cnt/lst
-    for (int idx = threadIdx.x; idx < PCL_CELLS * PCL_CELLS; idx += PCL_THREADS) cnt[idx] = 0;
-    if (threadIdx.x == 0) overflow = 0;
     __syncthreads();
+    const int ri0 = box[0], ri1 = box[1], rj0 = box[2], rj1 = box[3];
+    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
+    const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
     // 2. binning
     {
       const float inv_rw = 1.0f / (float)rw;
