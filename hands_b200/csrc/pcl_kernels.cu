@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
                                                               int crops_per_img, int R, float* __restrict__ out, int max_rows, int smem_bytes, int tma_ok) {
   extern __shared__ __align__(16) float4 mid4[];  // [nrows][s] pixels, channels in .x .y .z .w; then the staged source tile
   __shared__ int reg[5];                          // staged source region: x0, y0, ncols, nrows, staged?
+  __shared__ float4 rowrec[PCL_TR];               // per output row of the tile: ly0, ly1, offsets of its two source rows
   __shared__ uint64_t src_bar;
   const int q = blockIdx.y;
   const Crop c = load_crop(params + (size_t)q * PF);
@@ -239,24 +240,34 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
       }
       mid4[idx] = make_float4(v[0], v[1], v[2], v[3]);
     }
+    if (threadIdx.x < y1 - y0 + 1) {   // per-row resize coefficients of this tile, once per CTA
+      int a0, a1;
+      float ly0, ly1;
+      resize_coef(c, y0 + threadIdx.x, R, a0, a1, ly0, ly1);
+      rowrec[threadIdx.x] = make_float4(ly0, ly1, __int_as_float((a0 - jlo) * s), __int_as_float((a1 - jlo) * s));
+    }
     __syncthreads();
     for (int x = threadIdx.x; x < R; x += PCL_THREADS) {
       int b0, b1;
       float lx0, lx1;
       resize_coef(c, x, R, b0, b1, lx0, lx1);
-      // s <= R here, so the source row index advances by 0 or 1 per output row: keep the two live intermediate
-      // rows in registers and shift when it advances (block-uniform control flow)
-      int a0, a1;
-      float ly0, ly1;
-      resize_coef(c, y0, R, a0, a1, ly0, ly1);
-      const float4* row = mid4 + (a0 - jlo) * s;
-      float4 m00 = row[b0], m01 = row[b1];
-      row = mid4 + (a1 - jlo) * s;
-      float4 m10 = row[b0], m11 = row[b1];
+      // the two live intermediate rows stay in registers and are shifted / reloaded only when the source row index
+      // of the next output row changes (block-uniform control flow)
+      int cur0 = -1, cur1 = -1;
+      float4 m00 = make_float4(0.f, 0.f, 0.f, 0.f), m01 = m00, m10 = m00, m11 = m00;
       float* op = dst + (size_t)y0 * R + x;
+      const int nout = y1 - y0 + 1;
 #pragma unroll 1
-      for (int y = y0; y <= y1; ++y, op += R) {
-        const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1), w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
+      for (int t = 0; t < nout; ++t, op += R) {
+        const float4 rr = rowrec[t];
+        const int o0r = __float_as_int(rr.z), o1r = __float_as_int(rr.w);
+        if (o0r != cur0) {
+          if (o0r == cur1) { m00 = m10; m01 = m11; }
+          else { m00 = mid4[o0r + b0]; m01 = mid4[o0r + b1]; }
+          cur0 = o0r;
+        }
+        if (o1r != cur1) { m10 = mid4[o1r + b0]; m11 = mid4[o1r + b1]; cur1 = o1r; }
+        const float w00 = __fmul_rn(rr.x, lx0), w01 = __fmul_rn(rr.x, lx1), w10 = __fmul_rn(rr.y, lx0), w11 = __fmul_rn(rr.y, lx1);
         float o0 = __fmul_rn(w01, m01.x), o1 = __fmul_rn(w01, m01.y), o2 = __fmul_rn(w01, m01.z), o3 = __fmul_rn(w01, m01.w);
         o0 = fmaf(w00, m00.x, o0); o1 = fmaf(w00, m00.y, o1); o2 = fmaf(w00, m00.z, o2); o3 = fmaf(w00, m00.w, o3);
         o0 = fmaf(w10, m10.x, o0); o1 = fmaf(w10, m10.y, o1); o2 = fmaf(w10, m10.z, o2); o3 = fmaf(w10, m10.w, o3);
@@ -265,16 +276,6 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
         if (C > 1) __stcs(op + plane, o1);
         if (C > 2) __stcs(op + 2 * plane, o2);
         if (C > 3) __stcs(op + 3 * plane, o3);
-        if (y < y1) {
-          int n0, n1;
-          resize_coef(c, y + 1, R, n0, n1, ly0, ly1);
-          if (n0 != a0) {   // the source row advanced
-            if (n0 == a1) { m00 = m10; m01 = m11; }
-            else { const float4* nr = mid4 + (n0 - jlo) * s; m00 = nr[b0]; m01 = nr[b1]; }
-            if (n1 != a1) { const float4* nr = mid4 + (n1 - jlo) * s; m10 = nr[b0]; m11 = nr[b1]; }
-            a0 = n0; a1 = n1;
-          }
-        }
       }
     }
     return;
