@@ -423,9 +423,10 @@ constexpr int PCL_NS = 4;    // ring stages
 constexpr int PCL_NP = 4;    // columns per thread (s <= PCL_MT * PCL_NP on the fast path)
 static_assert(PCL_RB == 2, "the streaming transposed resize processes the two rows of a stage together");
 
-template <int C>
+template <int C, int RT>   // RT: image resolution known at compile time (0 = use the runtime argument)
 __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
-                                                             int q_base, int R, float* __restrict__ ws, int use_tma) {
+                                                             int q_base, int R_arg, float* __restrict__ ws, int use_tma) {
+  const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) float sm[];
   const int q = q_base + blockIdx.y;
   const float* rec = params + (size_t)q * PF;
@@ -841,7 +842,8 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + 2 * PCL_NS + (size_t)PCL_NS * C * PCL_RB * R);
   // bulk copies need 16-byte aligned rows: R % 4 == 0 and a 16-byte aligned g_out
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
-  HB_CUDA(cudaFuncSetAttribute(pcl_bwd_mid_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
+  auto mid_kernel = (R == 224) ? pcl_bwd_mid_kernel<C, 224> : pcl_bwd_mid_kernel<C, 0>;
+  HB_CUDA(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
   const size_t smem_img = (size_t)PCL_REG * 24 + (size_t)PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K);
   HB_CUDA(cudaFuncSetAttribute(pcl_bwd_img_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
@@ -850,7 +852,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
     dim3 g1((R + PCL_JR - 1) / PCL_JR, nim * crops_per_img);
     if (stages & 1) {
-      pcl_bwd_mid_kernel<C><<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
+      mid_kernel<<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
       g_launches++;
       rc = check_launch("pcl_bwd_mid_kernel");
       if (rc) return rc;
