@@ -113,9 +113,10 @@ __device__ __forceinline__ int fast_div(int idx, int s, float inv_s) {
 //            channel-interleaved so one LDS.128 fetches a pixel;
 //   phase 2: thread = output column, walking down the tile's rows; the two intermediate rows in use stay in
 //            registers while consecutive output rows share them (up-sampling), stores are coalesced rows.
-template <int C>
+template <int C, int RT>   // RT: image resolution known at compile time (0 = use the runtime argument)
 __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __restrict__ img, const float* __restrict__ params,
-                                                              int crops_per_img, int R, float* __restrict__ out, int max_rows, int smem_bytes, int tma_ok) {
+                                                              int crops_per_img, int R_arg, float* __restrict__ out, int max_rows, int smem_bytes, int tma_ok) {
+  const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) float4 mid4[];  // [nrows][s] pixels, channels in .x .y .z .w; then the staged source tile
   __shared__ int reg[5];                          // staged source region: x0, y0, ncols, nrows, staged?
   __shared__ float4 rowrec[PCL_TR];               // per output row of the tile: ly0, ly1, offsets of its two source rows
@@ -609,9 +610,10 @@ constexpr int PCL_REG = 2048;           // region pixels staged in shared memory
 //   3. every source pixel reads the <= 4 cells whose bilinear footprint covers it and accumulates exactly its
 //      contributors, in index order (so the result does not depend on the order the atomics ran in).
 // g_img is written once per pixel: no float atomics, no memset.
-template <int C>
+template <int C, int RT>
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
-                                                                  int img_base, int crops_per_img, int R, float* __restrict__ g_img) {
+                                                                  int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img) {
+  const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) uint8_t img_sm[];
   float4* ent_g = reinterpret_cast<float4*>(img_sm);                                   // [PCL_REG] staged region: gradient ...
   float2* ent_p = reinterpret_cast<float2*>(img_sm + PCL_REG * 16);                    // [PCL_REG] ... and sample position
@@ -786,9 +788,10 @@ static int launch_fwd(const float* img, const float* params, int n_crops, int cr
   static int want_tma = -1;
   if (want_tma < 0) { const char* e = getenv("HB_PCL_TMA"); want_tma = (e && e[0] == '0') ? 0 : 1; }
   const int tma_ok = want_tma && (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
-  HB_CUDA(cudaFuncSetAttribute(pcl_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
+  HB_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((R + PCL_TR - 1) / PCL_TR, n_crops);
-  pcl_fwd_kernel<C><<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, max_rows, (int)smem, tma_ok);
+  fwd_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, max_rows, (int)smem, tma_ok);
   g_launches++;
   return check_launch("pcl_fwd_kernel");
 }
@@ -846,7 +849,8 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   HB_CUDA(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
   const size_t smem_img = (size_t)PCL_REG * 24 + (size_t)PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K);
-  HB_CUDA(cudaFuncSetAttribute(pcl_bwd_img_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
+  auto img_kernel = (R == 224) ? pcl_bwd_img_kernel<C, 224> : pcl_bwd_img_kernel<C, 0>;
+  HB_CUDA(cudaFuncSetAttribute(img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int im0 = ch * chunk_imgs;
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
@@ -859,7 +863,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     }
     dim3 g2(tiles, nim);
     if (stages & 2) {
-      pcl_bwd_img_kernel<C><<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img);
+      img_kernel<<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img);
       g_launches++;
       rc = check_launch("pcl_bwd_img_kernel");
       if (rc) return rc;
