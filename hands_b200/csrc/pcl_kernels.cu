@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
   const int im = img_base + blockIdx.y;
-  const int lx = threadIdx.x & 31, lyb = threadIdx.x >> 5;  // 32 x 8 threads, 4 rows each
+  const int lx = threadIdx.x & 31, lyb = threadIdx.x >> 5;  // 32 x 8 threads, 4 adjacent rows each
   float acc[4][C];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -724,49 +724,66 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
       }
     }
     __syncthreads();
-    // 3. gather
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int ly = lyb + 8 * r;
-      const int sx = tx0 + lx, sy = ty0 + ly;
-      if (sx >= R || sy >= R) continue;
-      const float fsx = (float)sx, fsy = (float)sy;
+    // 3. gather.  A thread owns four vertically adjacent pixels (rows 4*lyb .. 4*lyb+3 of column lx): they touch five
+    //    rows of two cells; each cell's entries are read once and feed the pixel below (as its upper taps) and the
+    //    pixel above (as its lower taps).  Fixed order: cell row, cell column, list position.
+    {
+      const int sx = tx0 + lx;
+      const float fsx = (float)sx;
+      const int ly0 = 4 * lyb;
       if (!slow) {
+        if (sx < R) {
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
+          for (int cr = 0; cr < 5; ++cr) {
 #pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const int cell = (ly + dy) * PCL_CELLS + (lx + dx);  // floor(pos) == (sx-1+dx, sy-1+dy)
-            const int n = cnt[cell];
-            for (int e = 0; e < n; ++e) {
-              const int cur = lst[cell * PCL_K + e];
-              const float2 p = ent_p[cur];
-              const float4 g = ent_g[cur];
-              const float w = (1.0f - fabsf(p.x - fsx)) * (1.0f - fabsf(p.y - fsy));
+            for (int dx = 0; dx < 2; ++dx) {
+              const int cell = (ly0 + cr) * PCL_CELLS + (lx + dx);  // floor(pos) == (sx-1+dx, ty0+ly0+cr-1)
+              const int n = cnt[cell];
+              for (int e = 0; e < n; ++e) {
+                const int cur = lst[cell * PCL_K + e];
+                const float2 p = ent_p[cur];
+                const float4 g = ent_g[cur];
+                const float wx = 1.0f - fabsf(p.x - fsx);
+                const float gv[4] = {g.x, g.y, g.z, g.w};
+                if (cr < 4) {   // pixel row cr: floor(pos.y) == sy - 1
+                  const float w = wx * (1.0f - fabsf(p.y - (float)(ty0 + ly0 + cr)));
+#pragma unroll
+                  for (int ch = 0; ch < C; ++ch) acc[cr][ch] = fmaf(w, gv[ch], acc[cr][ch]);
+                }
+                if (cr > 0) {   // pixel row cr-1: floor(pos.y) == sy
+                  const float w = wx * (1.0f - fabsf(p.y - (float)(ty0 + ly0 + cr - 1)));
+#pragma unroll
+                  for (int ch = 0; ch < C; ++ch) acc[cr - 1][ch] = fmaf(w, gv[ch], acc[cr - 1][ch]);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // a cell list overflowed or the region did not fit (extreme foreshortening): scan the whole region
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int sy = ty0 + ly0 + r;
+          if (sx >= R || sy >= R) continue;
+          const float fsy = (float)sy;
+          for (int j = rj0; j <= rj1; ++j)
+            for (int i = ri0; i <= ri1; ++i) {
+              const float2 p = __ldg(POS + (size_t)j * s + i);
+              const float ax = fabsf(p.x - fsx), ay = fabsf(p.y - fsy);
+              if (!(ax < 1.0f && ay < 1.0f)) continue;
+              const float4 g = __ldg(G + (size_t)j * s + i);
+              const float w = (1.0f - ax) * (1.0f - ay);
               const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
               for (int ch = 0; ch < C; ++ch) acc[r][ch] = fmaf(w, gv[ch], acc[r][ch]);
             }
-          }
-      } else {
-        // a cell list overflowed (extreme foreshortening): scan the whole region for this tile and crop
-        for (int j = rj0; j <= rj1; ++j)
-          for (int i = ri0; i <= ri1; ++i) {
-            const float2 p = __ldg(POS + (size_t)j * s + i);
-            const float ax = fabsf(p.x - fsx), ay = fabsf(p.y - fsy);
-            if (!(ax < 1.0f && ay < 1.0f)) continue;
-            const float4 g = __ldg(G + (size_t)j * s + i);
-            const float w = (1.0f - ax) * (1.0f - ay);
-            const float gv[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) acc[r][ch] = fmaf(w, gv[ch], acc[r][ch]);
-          }
+        }
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const int sx = tx0 + lx, sy = ty0 + lyb + 8 * r;
+    const int sx = tx0 + lx, sy = ty0 + 4 * lyb + r;
     if (sx >= R || sy >= R) continue;
     float* op = g_img + (size_t)im * C * R * R + sy * R + sx;
 #pragma unroll
