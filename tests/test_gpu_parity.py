@@ -298,6 +298,50 @@ def test_pcl_forward_backward_against_oracle(dev, B, cpi, res, smooth):
     assert rel(g_img, ref_g) <= 1e-4
 
 
+@pytest.mark.parametrize("res,C", [(50, 3), (96, 1), (64, 4)])
+def test_pcl_generic_paths(dev, res, C):
+    """Resolutions that are not a multiple of 4 (no 16-byte aligned rows -> no bulk copies, generic transposed
+    resize) and channel counts other than 3 go through the fallback code paths; same tolerances."""
+    from hands_b200.functional import PerspectiveCropFunction
+
+    B = 3
+    img, bbox, K = synthetic_pcl_inputs(B, seed=res, img_res=res, smin=res // 4, smax=3 * res // 4)
+    g = torch.Generator().manual_seed(res)
+    img = torch.randn(B, C, res, res, generator=g)
+    w = torch.randn(B, C, res, res, generator=g)
+    x = img.to(dev).requires_grad_(True)
+    crop, rot = PerspectiveCropFunction.apply(x, bbox.to(dev), K.to(dev), 1)
+    (g_img,) = torch.autograd.grad((crop * w.to(dev)).sum(), x)
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        xr = img.clone().requires_grad_(True)
+        ref_crop, ref_rot = O.perspective_crop(xr, bbox, K, res)
+        (ref_g,) = torch.autograd.grad((ref_crop * w).sum(), xr)
+    finally:
+        torch.set_num_threads(nt)
+    assert (rot.cpu() - ref_rot).abs().max() <= 1.2e-7
+    assert (crop.detach().cpu() - ref_crop.detach()).abs().max() <= 5e-5
+    assert rel(g_img, ref_g) <= 1e-4
+
+
+def test_zero_batch_and_error_paths(dev):
+    from hands_b200 import _lib
+    from hands_b200.common import rot
+
+    lib = _lib.load()
+    assert rot.matrix_to_axis_angle(torch.empty(0, 3, 3, device=dev)).shape == (0, 3)
+    # workspace too small -> HB_E_WORKSPACE with a message, no launch
+    r = torch.eye(3, device=dev).repeat(2, 16, 1, 1).contiguous()
+    b = torch.zeros(2, 10, device=dev)
+    ws = torch.empty(16, device=dev)
+    import ctypes
+    P = ctypes.c_void_p
+    rc = lib.hb_mano_head_fwd(P(1), P(r.data_ptr()), 1, None, P(b.data_ptr()), None, None, None, 2, 224.0, 0.1,
+                              None, None, None, None, None, None, P(ws.data_ptr()), 64, None)
+    assert rc == -3 and b"workspace" in lib.hb_last_error_string()
+
+
 def test_no_cpu_fallback():
     from hands_b200.common import rot
 
