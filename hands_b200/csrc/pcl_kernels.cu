@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
 constexpr int PCL_TS = 32;              // source tile side
 constexpr int PCL_CELLS = PCL_TS + 1;   // cells = floor(sample position) in [tile-1, tile+31]
 constexpr int PCL_K = 4;                // list capacity per cell (longer lists take the scan fallback)
-constexpr int PCL_REG = 2048;           // region pixels staged in shared memory per (tile, crop)
+constexpr int PCL_REG = 1536;           // region pixels staged in shared memory per (tile, crop) (39 x 39; 4 CTAs/SM)
 
 // Transposed grid_sample, gather form.  One CTA per (image, 32x32 source tile); for each crop of the image:
 //   1. the tile's pre-image under the inverse homography bounds a region of the intermediate grid;
