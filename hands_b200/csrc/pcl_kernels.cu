@@ -420,12 +420,12 @@ __device__ __forceinline__ void transposed_taps(const float* __restrict__ src, s
 // of y ends the finished row is written out together with its sample positions.  No intermediate buffer, no
 // second pass: every g_out element is read from DRAM once (band overlap re-reads hit L2).
 constexpr int PCL_MT = 64;   // threads per CTA
-constexpr int PCL_NS = 4;    // ring stages
+constexpr int PCL_NS = 3;    // ring stages
 constexpr int PCL_NP = 4;    // columns per thread (s <= PCL_MT * PCL_NP on the fast path)
 static_assert(PCL_RB == 2, "the streaming transposed resize processes the two rows of a stage together");
 
 template <int C, int RT>   // RT: image resolution known at compile time (0 = use the runtime argument)
-__global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
+__global__ void __launch_bounds__(PCL_MT, 12) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
                                                              int q_base, int R_arg, float* __restrict__ ws, int use_tma) {
   const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) float sm[];
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
   float* tl1 = sm;                                   // [R]
   int* start = reinterpret_cast<int*>(sm + R);       // [R+1]  (s <= R on this path)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * R + 4);   // [PCL_NS]
-  float* stage = sm + 2 * R + 4 + 2 * PCL_NS;        // [PCL_NS][C][PCL_RB][R]  (16-byte aligned when R % 4 == 0)
+  float* stage = sm + 2 * R + 4 + ((2 * PCL_NS + 3) & ~3);   // [PCL_NS][C][PCL_RB][R]  (16-byte aligned when R % 4 == 0)
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
   float2* POS = reinterpret_cast<float2*>(base + 4 * (size_t)s * s);
@@ -859,7 +859,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     rc = check_launch("pcl_offsets_kernel");
     if (rc) return rc;
   }
-  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + 2 * PCL_NS + (size_t)PCL_NS * C * PCL_RB * R);
+  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + ((2 * PCL_NS + 3) & ~3) + (size_t)PCL_NS * C * PCL_RB * R);
   // bulk copies need 16-byte aligned rows: R % 4 == 0 and a 16-byte aligned g_out
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
   auto mid_kernel = (R == 224) ? pcl_bwd_mid_kernel<C, 224> : pcl_bwd_mid_kernel<C, 0>;
