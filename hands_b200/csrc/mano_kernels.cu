@@ -262,13 +262,13 @@ __device__ __forceinline__ void blend_transforms(const float* __restrict__ Ah, c
 struct SkinFwdOut { float* vertices; float* v3d; float* joints3d; float* j3d_cam; float* j2d; };
 
 template <bool USE_VP>
-__global__ void __launch_bounds__(VPB) mano_skin_fwd_kernel(ManoConst c, const float* __restrict__ ws, const float* __restrict__ Kmat,
+__global__ void __launch_bounds__(VPB, USE_VP ? 5 : 3) mano_skin_fwd_kernel(ManoConst c, const float* __restrict__ ws, const float* __restrict__ Kmat,
                                                             int B, float img_res, SkinFwdOut o, const float* __restrict__ vp) {
   extern __shared__ __align__(16) float smem[];
-  float* Fs = smem;                 // [FS][HBF]
-  float* As = Fs + FS * HBF;        // [HBF][AS]
-  float* Os = As + HBF * AS;        // [HBF][8]
-  float* Xs = Os + HBF * 8;         // [HBF][XS]
+  float* Fs = smem;                                // [FS][HBF]  (not needed in tensor-core mode)
+  float* As = Fs + (USE_VP ? 0 : FS * HBF);        // [HBF][AS]
+  float* Os = As + HBF * AS;                       // [HBF][8]
+  float* Xs = Os + HBF * 8;                        // [HBF][XS]
   const int tid = threadIdx.x;
   const int g = blockIdx.x, slice = blockIdx.y;
   const int v = slice * VPB + tid;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(VPB) mano_skin_fwd_kernel(ManoConst c, const f
     const float4* srcF = reinterpret_cast<const float4*>(ws + ws_F(B) + (size_t)g * FS * HBF);
     const float4* srcA = reinterpret_cast<const float4*>(ws + ws_A(B) + (size_t)g * HBF * AS);
     const float4* srcO = reinterpret_cast<const float4*>(ws + ws_OFF(B) + (size_t)g * HBF * 8);
-    for (int idx = tid; idx < FS * HBF / 4; idx += VPB) reinterpret_cast<float4*>(Fs)[idx] = srcF[idx];
+    if (!USE_VP) for (int idx = tid; idx < FS * HBF / 4; idx += VPB) reinterpret_cast<float4*>(Fs)[idx] = srcF[idx];
     for (int idx = tid; idx < HBF * AS / 4; idx += VPB) reinterpret_cast<float4*>(As)[idx] = srcA[idx];
     for (int idx = tid; idx < HBF * 8 / 4; idx += VPB) reinterpret_cast<float4*>(Os)[idx] = srcO[idx];
   }
@@ -357,7 +357,7 @@ constexpr int HSUB = 8;           // hands per reduction pass of the backward ke
 constexpr int GPS = HSUB + 0;     // g_p tile row length (hand fastest)
 
 template <bool USE_VP>
-__global__ void __launch_bounds__(VPB) mano_skin_bwd_kernel(ManoConst c, float* __restrict__ ws, const float* __restrict__ Kmat,
+__global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(ManoConst c, float* __restrict__ ws, const float* __restrict__ Kmat,
                                                             int B, float img_res, SkinBwdIn gi, const float* __restrict__ vp,
                                                             float* __restrict__ gvh, float* __restrict__ gvl) {
   extern __shared__ __align__(16) float smem[];
@@ -873,6 +873,7 @@ static bool use_tc() {
 }
 
 static const size_t kSkinFwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + HBF * XS);
+static const size_t kSkinFwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + HBF * XS);
 static const size_t kSkinBwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + 2 * HSUB * XS + VPB * 3 * HSUB + HSUB * 8);
 static const size_t kSkinBwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + 2 * HSUB * XS + HSUB * 8);
 
@@ -902,8 +903,8 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is
   if (tc) {
     rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
     if (rc) return rc;
-    HB_CUDA(cudaFuncSetAttribute(mano_skin_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinFwdSmem));
-    mano_skin_fwd_kernel<true><<<grid, VPB, kSkinFwdSmem, st>>>(h->c, ws, K, B, img_res, o, vpo);
+    HB_CUDA(cudaFuncSetAttribute(mano_skin_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinFwdSmemTc));
+    mano_skin_fwd_kernel<true><<<grid, VPB, kSkinFwdSmemTc, st>>>(h->c, ws, K, B, img_res, o, vpo);
   } else {
     HB_CUDA(cudaFuncSetAttribute(mano_skin_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinFwdSmem));
     mano_skin_fwd_kernel<false><<<grid, VPB, kSkinFwdSmem, st>>>(h->c, ws, K, B, img_res, o, nullptr);
