@@ -422,21 +422,22 @@ __device__ __forceinline__ void transposed_taps(const float* __restrict__ src, s
   }
 }
 
-// Transposed resize (g_out -> intermediate gradient), streaming form.
-// One CTA (PCL_MT threads) per (crop, band of PCL_JR intermediate rows).  The output rows the band needs are
-// streamed through a PCL_NS-stage shared-memory ring by bulk copies (one elected thread issues them, an mbarrier
-// per stage completes on the byte count).  Thread = intermediate column i: for each streamed row y it forms
-//   h = sum_{x in window(i)} wx(x,i) g_out[y][x]        (window = run(i-1) U run(i), contiguous)
-// and adds (1-l1[y]) h to the accumulator of intermediate row i0(y) and l1[y] h to the one of i0(y)+1; when a run
-// of y ends the finished row is written out together with its sample positions.  No intermediate buffer, no
-// second pass: every g_out element is read from DRAM once (band overlap re-reads hit L2).
-constexpr int PCL_MT = 64;   // threads per CTA
+// Transposed resize (g_out -> intermediate gradient), vertical-first streaming form.
+// One CTA (256 threads) per (crop, band of PCL_JR intermediate rows).  The output rows the band needs are streamed
+// through a PCL_NS-stage shared-memory ring by TMA bulk copies (one elected thread issues them; an mbarrier per stage
+// completes on the byte count).
+//   vertical pass  : thread = OUTPUT column x.  For every streamed row y it adds (1-l1[y]) g[y][x] to the accumulator of
+//                    intermediate row i0(y) and l1[y] g[y][x] to the one of i0(y)+1 -- six FMAs per element, conflict-free
+//                    shared-memory reads, every g_out element touched once.
+//   horizontal pass: when the run of y belonging to an intermediate row ends, the finished row V[x] is parked in shared
+//                    memory and thread = INTERMEDIATE column i reduces its contiguous window run(i-1) U run(i); the row
+//                    is written out with its sample positions.  The windowed reduction runs once per intermediate row
+//                    (s of them) instead of once per output row (R of them).
+constexpr int PCL_MT = 256;  // threads per CTA
 constexpr int PCL_NS = 3;    // ring stages
-constexpr int PCL_NP = 4;    // columns per thread (s <= PCL_MT * PCL_NP on the fast path)
-static_assert(PCL_RB == 2, "the streaming transposed resize processes the two rows of a stage together");
 
 template <int C, int RT>   // RT: image resolution known at compile time (0 = use the runtime argument)
-__global__ void __launch_bounds__(PCL_MT, 12) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
+__global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
                                                              int q_base, int R_arg, float* __restrict__ ws, int use_tma) {
   const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) float sm[];
@@ -451,13 +452,14 @@ __global__ void __launch_bounds__(PCL_MT, 12) pcl_bwd_mid_kernel(const float* __
   int* start = reinterpret_cast<int*>(sm + R);       // [R+1]  (s <= R on this path)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * R + 4);   // [PCL_NS]
   float* stage = sm + 2 * R + 4 + ((2 * PCL_NS + 3) & ~3);   // [PCL_NS][C][PCL_RB][R]  (16-byte aligned when R % 4 == 0)
+  float* Vs = stage + PCL_NS * C * PCL_RB * R;       // [C][R] one finished intermediate row, still at output-column resolution
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
   float2* POS = reinterpret_cast<float2*>(base + 4 * (size_t)s * s);
   const float* go = g_out + (size_t)q * C * R * R;
   const float Rf = (float)R;
   const int tid = threadIdx.x;
-  if (s <= R && s <= PCL_MT * PCL_NP && use_tma) {
+  if (s <= R && R <= PCL_MT && use_tma) {
     if (tid == 0) {
 #pragma unroll
       for (int k = 0; k < PCL_NS; ++k) mbar_init(&bars[k], 1);
@@ -480,103 +482,76 @@ __global__ void __launch_bounds__(PCL_MT, 12) pcl_bwd_mid_kernel(const float* __
     if (tid == 0) {
       for (int b = 0; b < min(nblk, PCL_NS); ++b) issue(b);
     }
-    // per-thread columns: window [wb, we) with the split point wa (d < wa: weight l1[d], else 1-l1[d]; the last
-    // column gets weight 1 on its own run because the upper source index is clamped there)
-    int wb[PCL_NP], wa[PCL_NP], we[PCL_NP];
-    float cur[PCL_NP][C], nxt[PCL_NP][C];
+    // horizontal window of this thread's intermediate column i = tid: [wb, we), split at wa
+    // (d < wa: weight l1[d], else 1-l1[d]; the last column takes weight 1 on its own run, its upper index is clamped)
+    const bool col_on = tid < s;
+    const int wa = col_on ? start[tid] : 0;
+    const int we = col_on ? start[tid + 1] : 0;
+    const int wb = col_on ? (tid > 0 ? start[tid - 1] : wa) : 0;
+    const bool last_col = tid == s - 1;
+    const bool x_on = tid < R;
+    float cur[C], nxt[C];
 #pragma unroll
-    for (int p = 0; p < PCL_NP; ++p) {
-      const int i = tid + p * PCL_MT;
-      const bool on = i < s;
-      wa[p] = on ? start[i] : 0;
-      we[p] = on ? start[i + 1] : 0;
-      wb[p] = on ? (i > 0 ? start[i - 1] : wa[p]) : 0;
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) { cur[p][ch] = 0.f; nxt[p][ch] = 0.f; }
-    }
+    for (int ch = 0; ch < C; ++ch) { cur[ch] = 0.f; nxt[ch] = 0.f; }
     int jc = jfirst;   // intermediate row the accumulators `cur` belong to (`nxt` belongs to jc+1)
-    auto emit = [&](int j) {
-      if (j < j0 || j > j1) return;
+    auto finish_row = [&](int j) {   // block-uniform
+      if (j >= j0 && j <= j1) {
+        if (x_on) {
 #pragma unroll
-      for (int p = 0; p < PCL_NP; ++p) {
-        const int i = tid + p * PCL_MT;
-        if (i < s) {
+          for (int ch = 0; ch < C; ++ch) Vs[ch * R + tid] = cur[ch];
+        }
+        __syncthreads();
+        if (col_on) {
+          float h[C];
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) h[ch] = 0.f;
+          for (int d = wb; d < wa; ++d) {
+            const float w = tl1[d];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, Vs[ch * R + d], h[ch]);
+          }
+          for (int d = wa; d < we; ++d) {
+            const float w = last_col ? 1.0f : 1.0f - tl1[d];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, Vs[ch * R + d], h[ch]);
+          }
           float ix, iy;
-          sample_pos_fast(c, j, i, Rf, ix, iy);
+          sample_pos_fast(c, j, tid, Rf, ix, iy);
           float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = cur[p][ch];
-          POS[(size_t)j * s + i] = make_float2(ix, iy);
-          G[(size_t)j * s + i] = make_float4(v[0], v[1], v[2], v[3]);
+          for (int ch = 0; ch < C; ++ch) v[ch] = h[ch];
+          POS[(size_t)j * s + tid] = make_float2(ix, iy);
+          G[(size_t)j * s + tid] = make_float4(v[0], v[1], v[2], v[3]);
         }
+        __syncthreads();   // Vs is reused by the next finished row
       }
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) { cur[ch] = nxt[ch]; nxt[ch] = 0.f; }
     };
     for (int b = 0; b < nblk; ++b) {
       const int stg = b % PCL_NS;
       mbar_wait(&bars[stg], (b / PCL_NS) & 1);
       const float* st = stage + (size_t)stg * C * PCL_RB * R;
       const int r0 = b * PCL_RB, nr = min(PCL_RB, nrows - r0);
-      // horizontal reduction of the block's (<= PCL_RB = 2) rows: weights and loop overhead are shared by the rows
-      float h[PCL_NP][2][C];
+      for (int rr = 0; rr < nr; ++rr) {
+        const int y = ylo + r0 + rr;
+        while (y >= start[jc + 1]) { finish_row(jc); ++jc; }   // run of jc finished (block-uniform)
+        const float ly1 = tl1[y];
+        const bool last_row = jc >= s - 1;
+        const float ly0 = last_row ? 1.0f : 1.0f - ly1;
+        if (x_on) {
 #pragma unroll
-      for (int p = 0; p < PCL_NP; ++p) {
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) { h[p][0][ch] = 0.f; h[p][1][ch] = 0.f; }
-        if (tid + p * PCL_MT < s) {
-          const bool last_col = tid + p * PCL_MT == s - 1;
-          for (int d = wb[p]; d < wa[p]; ++d) {
-            const float w = tl1[d];
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-              h[p][0][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + d], h[p][0][ch]);
-              h[p][1][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + R + d], h[p][1][ch]);
-            }
+          for (int ch = 0; ch < C; ++ch) {
+            const float gval = st[(ch * PCL_RB + rr) * R + tid];
+            cur[ch] = fmaf(ly0, gval, cur[ch]);
+            if (!last_row) nxt[ch] = fmaf(ly1, gval, nxt[ch]);
           }
-          for (int d = wa[p]; d < we[p]; ++d) {
-            const float w = last_col ? 1.0f : 1.0f - tl1[d];
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-              h[p][0][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + d], h[p][0][ch]);
-              h[p][1][ch] = fmaf(w, st[(size_t)ch * PCL_RB * R + R + d], h[p][1][ch]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < PCL_RB; ++rr) {
-        if (rr < nr) {
-          const int y = ylo + r0 + rr;
-          while (y >= start[jc + 1]) {   // run of jc finished (block-uniform)
-            emit(jc);
-#pragma unroll
-            for (int p = 0; p < PCL_NP; ++p)
-#pragma unroll
-              for (int ch = 0; ch < C; ++ch) { cur[p][ch] = nxt[p][ch]; nxt[p][ch] = 0.f; }
-            ++jc;
-          }
-          const float ly1 = tl1[y];
-          const bool last_row = jc >= s - 1;
-          const float ly0 = last_row ? 1.0f : 1.0f - ly1;
-#pragma unroll
-          for (int p = 0; p < PCL_NP; ++p)
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-              cur[p][ch] = fmaf(ly0, h[p][rr][ch], cur[p][ch]);
-              if (!last_row) nxt[p][ch] = fmaf(ly1, h[p][rr][ch], nxt[p][ch]);
-            }
         }
       }
       __syncthreads();   // everyone is done reading this stage
       if (tid == 0 && b + PCL_NS < nblk) { fence_proxy_async(); issue(b + PCL_NS); }
     }
-    while (jc <= j1) {   // flush: the band's last rows (also covers a clamped last row whose own run is empty)
-      emit(jc);
-#pragma unroll
-      for (int p = 0; p < PCL_NP; ++p)
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) { cur[p][ch] = nxt[p][ch]; nxt[p][ch] = 0.f; }
-      ++jc;
-    }
+    while (jc <= j1) { finish_row(jc); ++jc; }   // flush (also covers a clamped last row whose own run is empty)
     return;
   }
   // generic path (s > R, very large s, or unaligned rows): direct 2-D gather per intermediate pixel
@@ -873,7 +848,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     rc = check_launch("pcl_offsets_kernel");
     if (rc) return rc;
   }
-  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + ((2 * PCL_NS + 3) & ~3) + (size_t)PCL_NS * C * PCL_RB * R);
+  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + ((2 * PCL_NS + 3) & ~3) + (size_t)PCL_NS * C * PCL_RB * R + (size_t)C * R);
   // bulk copies need 16-byte aligned rows: R % 4 == 0 and a 16-byte aligned g_out
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
   auto mid_kernel = (R == 224) ? pcl_bwd_mid_kernel<C, 224> : pcl_bwd_mid_kernel<C, 0>;
