@@ -422,24 +422,25 @@ __device__ __forceinline__ void transposed_taps(const float* __restrict__ src, s
   }
 }
 
-// Transposed resize (g_out -> intermediate gradient), vertical-first streaming form.
-// One CTA (256 threads) per (crop, band of PCL_JR intermediate rows).  The output rows the band needs are streamed
-// through a PCL_NS-stage shared-memory ring by TMA bulk copies (one elected thread issues them; an mbarrier per stage
-// completes on the byte count).
-//   vertical pass  : thread = OUTPUT column x.  For every streamed row y it adds (1-l1[y]) g[y][x] to the accumulator of
-//                    intermediate row i0(y) and l1[y] g[y][x] to the one of i0(y)+1 -- six FMAs per element, conflict-free
-//                    shared-memory reads, every g_out element touched once.
-//   horizontal pass: when the run of y belonging to an intermediate row ends, the finished row V[x] is parked in shared
-//                    memory and thread = INTERMEDIATE column i reduces its contiguous window run(i-1) U run(i); the row
-//                    is written out with its sample positions.  The windowed reduction runs once per intermediate row
-//                    (s of them) instead of once per output row (R of them).
+// Transposed resize (g_out -> intermediate gradient), vertical-first form.
+// One CTA (256 threads) per (crop, band of PCL_JR intermediate rows).
+//   vertical pass  : thread = OUTPUT column x walks down the output rows the band needs, reading g_out straight from
+//                    global memory (a warp reads 128 contiguous bytes per row and channel; four rows are in flight per
+//                    thread).  Row y adds (1-l1[y]) g to the accumulator of intermediate row i0(y) and l1[y] g to the one
+//                    of i0(y)+1 -- six FMAs per element, no barrier; a finished row is parked in this thread's column of
+//                    the band buffer in shared memory.
+//   horizontal pass: after one barrier, thread = (intermediate row, intermediate column) reduces its contiguous window
+//                    run(i-1) U run(i) of the band buffer and writes the gradient with its sample position.  The windowed
+//                    reduction runs once per intermediate row (s of them) instead of once per output row (R of them).
+// (A variant that streamed the rows through a TMA-fed shared-memory ring measured slower, 4.10 ms vs this one: with only
+//  six FMAs per element the ring's per-stage barriers dominated.)
 constexpr int PCL_MT = 256;  // threads per CTA
-constexpr int PCL_NS = 3;    // ring stages
 
 template <int C, int RT>   // RT: image resolution known at compile time (0 = use the runtime argument)
 __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
                                                              int q_base, int R_arg, float* __restrict__ ws, int use_tma) {
   const int R = RT ? RT : R_arg;
+  (void)use_tma;
   extern __shared__ __align__(16) float sm[];
   const int q = q_base + blockIdx.y;
   const float* rec = params + (size_t)q * PF;
@@ -450,108 +451,87 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
   const int j1 = min(j0 + PCL_JR, s) - 1;
   float* tl1 = sm;                                   // [R]
   int* start = reinterpret_cast<int*>(sm + R);       // [R+1]  (s <= R on this path)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * R + 4);   // [PCL_NS]
-  float* stage = sm + 2 * R + 4 + ((2 * PCL_NS + 3) & ~3);   // [PCL_NS][C][PCL_RB][R]  (16-byte aligned when R % 4 == 0)
-  float* Vs = stage + PCL_NS * C * PCL_RB * R;       // [C][R] one finished intermediate row, still at output-column resolution
+  float* Vb = sm + 2 * R + 4;                        // [PCL_JR][C][R] finished intermediate rows at output-column resolution
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
   float2* POS = reinterpret_cast<float2*>(base + 4 * (size_t)s * s);
   const float* go = g_out + (size_t)q * C * R * R;
   const float Rf = (float)R;
   const int tid = threadIdx.x;
-  if (s <= R && R <= PCL_MT && use_tma) {
-    if (tid == 0) {
-#pragma unroll
-      for (int k = 0; k < PCL_NS; ++k) mbar_init(&bars[k], 1);
-      mbar_fence_init();
-    }
-    build_tables(c, R, tl1, start);   // contains the __syncthreads() that publishes the barrier init
+  if (s <= R) {
+    build_tables(c, R, tl1, start);
     const int jfirst = max(j0 - 1, 0);
     const int ylo = start[jfirst], yhi = start[j1 + 1];
-    const int nrows = yhi - ylo;
-    const int nblk = (nrows + PCL_RB - 1) / PCL_RB;
-    auto issue = [&](int b) {
-      const int r0 = b * PCL_RB, nr = min(PCL_RB, nrows - r0);
-      const int st = b % PCL_NS;
-      float* dst = stage + (size_t)st * C * PCL_RB * R;
-      const uint32_t bytes = (uint32_t)(nr * R * sizeof(float));
-      mbar_arrive_expect_tx(&bars[st], bytes * C);
+    const int plane = R * R;
+    for (int x = tid; x < R; x += PCL_MT) {
+      float cur[C], nxt[C];
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) bulk_g2s(dst + (size_t)ch * PCL_RB * R, go + ((size_t)ch * R + ylo + r0) * R, bytes, &bars[st]);
-    };
-    if (tid == 0) {
-      for (int b = 0; b < min(nblk, PCL_NS); ++b) issue(b);
-    }
-    // horizontal window of this thread's intermediate column i = tid: [wb, we), split at wa
-    // (d < wa: weight l1[d], else 1-l1[d]; the last column takes weight 1 on its own run, its upper index is clamped)
-    const bool col_on = tid < s;
-    const int wa = col_on ? start[tid] : 0;
-    const int we = col_on ? start[tid + 1] : 0;
-    const int wb = col_on ? (tid > 0 ? start[tid - 1] : wa) : 0;
-    const bool last_col = tid == s - 1;
-    const bool x_on = tid < R;
-    float cur[C], nxt[C];
+      for (int ch = 0; ch < C; ++ch) { cur[ch] = 0.f; nxt[ch] = 0.f; }
+      int jc = jfirst;   // intermediate row the accumulators `cur` belong to (`nxt` belongs to jc+1)
+      auto finish_row = [&](int j) {
+        if (j >= j0 && j <= j1) {
 #pragma unroll
-    for (int ch = 0; ch < C; ++ch) { cur[ch] = 0.f; nxt[ch] = 0.f; }
-    int jc = jfirst;   // intermediate row the accumulators `cur` belong to (`nxt` belongs to jc+1)
-    auto finish_row = [&](int j) {   // block-uniform
-      if (j >= j0 && j <= j1) {
-        if (x_on) {
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) Vs[ch * R + tid] = cur[ch];
+          for (int ch = 0; ch < C; ++ch) Vb[((j - j0) * C + ch) * R + x] = cur[ch];
         }
-        __syncthreads();
-        if (col_on) {
-          float h[C];
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) h[ch] = 0.f;
-          for (int d = wb; d < wa; ++d) {
-            const float w = tl1[d];
+        for (int ch = 0; ch < C; ++ch) { cur[ch] = nxt[ch]; nxt[ch] = 0.f; }
+      };
+      const float* gp = go + (size_t)ylo * R + x;
+      for (int y = ylo; y < yhi; y += 4, gp += 4 * R) {
+        float gv[4][C];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, Vs[ch * R + d], h[ch]);
-          }
-          for (int d = wa; d < we; ++d) {
-            const float w = last_col ? 1.0f : 1.0f - tl1[d];
+        for (int u = 0; u < 4; ++u)   // four rows in flight
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, Vs[ch * R + d], h[ch]);
-          }
-          float ix, iy;
-          sample_pos_fast(c, j, tid, Rf, ix, iy);
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int ch = 0; ch < C; ++ch) gv[u][ch] = (y + u < yhi) ? __ldcs(gp + u * R + ch * plane) : 0.f;
 #pragma unroll
-          for (int ch = 0; ch < C; ++ch) v[ch] = h[ch];
-          POS[(size_t)j * s + tid] = make_float2(ix, iy);
-          G[(size_t)j * s + tid] = make_float4(v[0], v[1], v[2], v[3]);
-        }
-        __syncthreads();   // Vs is reused by the next finished row
-      }
+        for (int u = 0; u < 4; ++u) {
+          const int yy = y + u;
+          if (yy < yhi) {
+            while (yy >= start[jc + 1]) { finish_row(jc); ++jc; }   // run of jc finished (block-uniform)
+            const float ly1 = tl1[yy];
+            const bool last_row = jc >= s - 1;
+            const float ly0 = last_row ? 1.0f : 1.0f - ly1;
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) { cur[ch] = nxt[ch]; nxt[ch] = 0.f; }
-    };
-    for (int b = 0; b < nblk; ++b) {
-      const int stg = b % PCL_NS;
-      mbar_wait(&bars[stg], (b / PCL_NS) & 1);
-      const float* st = stage + (size_t)stg * C * PCL_RB * R;
-      const int r0 = b * PCL_RB, nr = min(PCL_RB, nrows - r0);
-      for (int rr = 0; rr < nr; ++rr) {
-        const int y = ylo + r0 + rr;
-        while (y >= start[jc + 1]) { finish_row(jc); ++jc; }   // run of jc finished (block-uniform)
-        const float ly1 = tl1[y];
-        const bool last_row = jc >= s - 1;
-        const float ly0 = last_row ? 1.0f : 1.0f - ly1;
-        if (x_on) {
-#pragma unroll
-          for (int ch = 0; ch < C; ++ch) {
-            const float gval = st[(ch * PCL_RB + rr) * R + tid];
-            cur[ch] = fmaf(ly0, gval, cur[ch]);
-            if (!last_row) nxt[ch] = fmaf(ly1, gval, nxt[ch]);
+            for (int ch = 0; ch < C; ++ch) {
+              cur[ch] = fmaf(ly0, gv[u][ch], cur[ch]);
+              if (!last_row) nxt[ch] = fmaf(ly1, gv[u][ch], nxt[ch]);
+            }
           }
         }
       }
-      __syncthreads();   // everyone is done reading this stage
-      if (tid == 0 && b + PCL_NS < nblk) { fence_proxy_async(); issue(b + PCL_NS); }
+      while (jc <= j1) { finish_row(jc); ++jc; }   // flush (also covers a clamped last row whose own run is empty)
     }
-    while (jc <= j1) { finish_row(jc); ++jc; }   // flush (also covers a clamped last row whose own run is empty)
+    __syncthreads();
+    const int nB = (j1 - j0 + 1) * s;
+    const float inv_s = 1.0f / (float)s;
+    for (int idx = tid; idx < nB; idx += PCL_MT) {
+      const int jr = fast_div(idx, s, inv_s), i = idx - jr * s;
+      const int j = j0 + jr;
+      // window [wb, we) split at wa: d < wa weighs l1[d], else 1-l1[d]; the last column takes weight 1 on its own run
+      const int wa = start[i], we = start[i + 1], wb = i > 0 ? start[i - 1] : wa;
+      const bool last_col = i == s - 1;
+      const float* vrow = Vb + (size_t)jr * C * R;
+      float h[C];
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) h[ch] = 0.f;
+      for (int d = wb; d < wa; ++d) {
+        const float w = tl1[d];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, vrow[ch * R + d], h[ch]);
+      }
+      for (int d = wa; d < we; ++d) {
+        const float w = last_col ? 1.0f : 1.0f - tl1[d];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, vrow[ch * R + d], h[ch]);
+      }
+      float ix, iy;
+      sample_pos_fast(c, j, i, Rf, ix, iy);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) v[ch] = h[ch];
+      POS[(size_t)j * s + i] = make_float2(ix, iy);
+      G[(size_t)j * s + i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
     return;
   }
   // generic path (s > R, very large s, or unaligned rows): direct 2-D gather per intermediate pixel
@@ -848,7 +828,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     rc = check_launch("pcl_offsets_kernel");
     if (rc) return rc;
   }
-  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + ((2 * PCL_NS + 3) & ~3) + (size_t)PCL_NS * C * PCL_RB * R + (size_t)C * R);
+  const size_t smem_mid = sizeof(float) * ((size_t)2 * R + 4 + (size_t)PCL_JR * C * R);
   // bulk copies need 16-byte aligned rows: R % 4 == 0 and a 16-byte aligned g_out
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
   auto mid_kernel = (R == 224) ? pcl_bwd_mid_kernel<C, 224> : pcl_bwd_mid_kernel<C, 0>;
