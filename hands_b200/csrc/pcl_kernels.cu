@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(1024) pcl_offsets_kernel(float* __restrict__ p
 }
 
 constexpr int PCL_JR = 16;  // intermediate rows per CTA
-constexpr int PCL_RB = 2;   // output rows per bulk-copy stage of the transposed resize
+
 
 // approximate sample position for the backward pass (the gradient is continuous in the position, so the
 // correctly-rounded divisions of the forward are not needed here)
