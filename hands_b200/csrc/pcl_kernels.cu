@@ -3,13 +3,17 @@
 // The reference runs, per sample on the CPU:  float64 homography -> fp32 grid (linspace, 3x3 matmul,
 // divide, normalise) -> F.grid_sample(bilinear, zeros, align_corners=False) to s x s ->
 // F.interpolate(bilinear, align_corners=True) to R x R.  Here:
-//   pcl_setup_kernel : the float64 homography, one thread per crop                  (lines 357-386, 425-454)
-//   pcl_fwd_kernel   : one CTA per (crop, 16 output rows): the needed rows of the s x s intermediate are
-//                      gathered once into shared memory, then resized from there; R x R stores coalesced.
-//   pcl_bwd_mid      : transposed resize, gather form  (g_out -> g_mid, the s x s intermediate gradient)
-//   pcl_bwd_img      : transposed grid_sample, gather form through the inverse homography: each source
-//                      pixel collects from the few intermediate pixels whose bilinear footprint covers it,
-//                      so g_img is written exactly once -- no atomics, no memset, deterministic.
+//   pcl_setup_kernel : the float64 homography, one thread per crop (pcl_setup.cu)    (lines 357-386, 425-454)
+//   pcl_fwd_kernel   : one CTA per (crop, 16 output rows), in sub-blocks that fit a 44 KB shared-memory budget:
+//                      the source footprint is staged by TMA bulk copies, the needed rows of the s x s intermediate
+//                      are gathered from it once, then resized from shared memory; R x R stores are coalesced rows.
+//   pcl_bwd_mid      : transposed resize, vertical pass first (thread = output column, rows straight from global),
+//                      then the windowed horizontal reduction once per intermediate row; writes the intermediate
+//                      gradient and the sample positions into the chunk workspace.
+//   pcl_bwd_img      : transposed grid_sample, gather form through the inverse homography: the region of the
+//                      intermediate grid that can reach a 32x32 source tile is staged with cp.async and binned into
+//                      per-cell lists; each source pixel collects exactly its contributors in a fixed order, so
+//                      g_img is written once -- no float atomics, no memset, bit-reproducible.
 // The fp32 operation order (which products are fused) follows torch's CPU kernels exactly; it was pinned
 // by bit-comparing a numpy emulation against torch 2.11 single-threaded ("PCL exactness").
 #include <climits>
