@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
 constexpr int PCL_WS_FLOATS_PER_PX = 6;
 
 // exclusive scan of the per-crop workspace sizes inside each chunk (one 1024-thread block per chunk)
-__global__ void __launch_bounds__(1024) pcl_offsets_kernel(float* __restrict__ params, int n_crops, int chunk_crops) {
+__global__ void __launch_bounds__(1024) pcl_offsets_kernel(float* __restrict__ params, int n_crops, int chunk_crops, int img_res) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
   const int q0 = blockIdx.x * chunk_crops;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(1024) pcl_offsets_kernel(float* __restrict__ p
     int sz = 0;
     if (q < q1) {
       const int s = __float_as_int(params[(size_t)q * PF + 18]);
-      sz = (PCL_WS_FLOATS_PER_PX * s * s + 3) & ~3;  // keep every crop's float4 array 16-byte aligned
+      sz = s > img_res ? 0 : ((PCL_WS_FLOATS_PER_PX * s * s + 3) & ~3);  // keep every crop's float4 array 16-byte aligned
     }
     int inc = sz;  // inclusive scan within the warp
 #pragma unroll
@@ -451,10 +451,10 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
   const Crop c = load_crop(rec);
   const int s = c.s;
   const int j0 = blockIdx.x * PCL_JR;
-  if (j0 >= s) return;
+  if (j0 >= s || s > R) return;   // s > R is outside the supported domain of the backward (workspace sized for s <= R)
   const int j1 = min(j0 + PCL_JR, s) - 1;
   float* tl1 = sm;                                   // [R]
-  int* start = reinterpret_cast<int*>(sm + R);       // [R+1]  (s <= R on this path)
+  int* start = reinterpret_cast<int*>(sm + R);       // [R+1]
   float* Vb = sm + 2 * R + 4;                        // [PCL_JR][C][R] finished intermediate rows at output-column resolution
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
@@ -607,6 +607,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     if (__float_as_int(__ldg(rec + 22)) > tx0 + PCL_TS || __float_as_int(__ldg(rec + 23)) < tx0 - 1 ||
         __float_as_int(__ldg(rec + 24)) > ty0 + PCL_TS || __float_as_int(__ldg(rec + 25)) < ty0 - 1) continue;
     const int s = __float_as_int(__ldg(rec + 18));
+    if (s > R) continue;   // outside the supported domain of the backward (see hb_pcl_bwd in the header)
     const float* base = ws + __float_as_int(__ldg(rec + 21));
     const float4* G = reinterpret_cast<const float4*>(base);
     const float2* POS = reinterpret_cast<const float2*>(base + 4 * (size_t)s * s);
@@ -827,7 +828,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const int n_chunks = (n_imgs + chunk_imgs - 1) / chunk_imgs;
   int rc = 0;
   if (stages & 1) {
-    pcl_offsets_kernel<<<n_chunks, 1024, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops);
+    pcl_offsets_kernel<<<n_chunks, 1024, 0, st>>>(const_cast<float*>(params), n_crops, chunk_crops, R);
     g_launches++;
     rc = check_launch("pcl_offsets_kernel");
     if (rc) return rc;

@@ -266,6 +266,13 @@ class PerspectiveCropFunction(torch.autograd.Function):
         if tuple(bbox.shape) != (n, 4):
             raise ValueError(f"bbox: expected ({n},4), got {tuple(bbox.shape)}")
         K = _f32c(K.to(dev) if isinstance(K, torch.Tensor) else K, "K", (n, 3, 3))
+        if img.requires_grad and n > 0:
+            # The backward packs an s x s intermediate per crop into a workspace sized for s <= R, which the reference
+            # guarantees by clipping boxes to the image (common/data_utils.py:508).  Fail loudly otherwise.
+            side = int((bbox[:, 2:] - bbox[:, :2]).max())
+            if side > R:
+                raise ValueError(f"perspective_crop backward needs boxes no larger than the image (side {side} > {R}); "
+                                 "clip the boxes or call under torch.no_grad()")
         params = torch.empty(n, _lib.PCL_PARAM_FLOATS, dtype=torch.float32, device=dev)
         rot = torch.empty(n, 3, 3, dtype=torch.float32, device=dev)
         out = torch.empty(n, C, R, R, dtype=torch.float32, device=dev)

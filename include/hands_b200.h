@@ -128,7 +128,9 @@ int hb_pcl_homography_host(const int32_t* bbox_host, const float* K_host, int im
  *   interpolate(bilinear, align_corners=True) to R x R, fused. out (n_crops, C, R, R). */
 int hb_pcl_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int C, int img_res,
                float* out, void* stream);
-/* Backward w.r.t. img (the grid is data).  g_out (n_crops,C,R,R) -> g_img (n_crops/crops_per_img,C,R,R),
+/* Backward w.r.t. img (the grid is data).  Domain: boxes no larger than the image (s <= img_res), which the reference
+ * guarantees by clipping boxes to the image (common/data_utils.py:508); a larger crop contributes no gradient here and
+ * the Python wrapper rejects it up front.  g_out (n_crops,C,R,R) -> g_img (n_crops/crops_per_img,C,R,R),
  *   written exactly once (no float atomics, deterministic).  The backward runs in chunks of images sized by the
  *   workspace given: hb_pcl_bwd_workspace_bytes() is the recommended size, any size >= one image's worth works. */
 size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int C, int img_res);

@@ -325,6 +325,30 @@ def test_pcl_generic_paths(dev, res, C):
     assert rel(g_img, ref_g) <= 1e-4
 
 
+def test_pcl_box_larger_than_image(dev):
+    """A box reaching outside the image gives s > img_res (down-sampling): the forward's generic code path."""
+    from hands_b200.pcl import perspective_crop
+
+    res = 64
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(2, 3, res, res, generator=g)
+    bbox = torch.tensor([[-10, -5, 90, 80], [5, -20, 60, 75]], dtype=torch.int32)
+    K = torch.tensor([[[80.0, 0, 32], [0, 80.0, 32], [0, 0, 1]], [[120.0, 0, 30], [0, 110.0, 33], [0, 0, 1]]])
+    with torch.no_grad():
+        crop, rot = perspective_crop(img.to(dev), bbox.to(dev), K.to(dev), img_res=res)
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        ref_crop, ref_rot = O.perspective_crop(img, bbox, K, res)
+    finally:
+        torch.set_num_threads(nt)
+    assert (rot.cpu() - ref_rot).abs().max() <= 1.2e-7
+    assert (crop.cpu() - ref_crop).abs().max() <= 5e-5
+    # the backward's workspace is sized for s <= img_res (the reference clips boxes to the image): rejected up front
+    with pytest.raises(ValueError, match="no larger than the image"):
+        perspective_crop(img.to(dev).requires_grad_(True), bbox.to(dev), K.to(dev), img_res=res)
+
+
 def test_zero_batch_and_error_paths(dev):
     from hands_b200 import _lib
     from hands_b200.common import rot
