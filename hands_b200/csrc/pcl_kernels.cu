@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
 
 // ---- backward -------------------------------------------------------------------------------------
 // Chunk workspace, per crop (offset params[21], in floats, a multiple of 4): G float4[s*s] intermediate
-// gradient (channels in x,y,z,w), then POS float2[s*s] sample positions.  6*s*s floats per crop.
-constexpr int PCL_WS_FLOATS_PER_PX = 6;
+// gradient (channels in x,y,z,w); 4*s*s floats per crop.  (Sample positions are recomputed by the consumer.)
+constexpr int PCL_WS_FLOATS_PER_PX = 4;
 
 // exclusive scan of the per-crop workspace sizes inside each chunk (one 1024-thread block per chunk)
 __global__ void __launch_bounds__(1024) pcl_offsets_kernel(float* __restrict__ params, int n_crops, int chunk_crops, int img_res) {
@@ -458,9 +458,7 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
   float* Vb = sm + 2 * R + 4;                        // [PCL_JR][C][R] finished intermediate rows at output-column resolution
   float* base = ws + __float_as_int(__ldg(rec + 21));
   float4* G = reinterpret_cast<float4*>(base);
-  float2* POS = reinterpret_cast<float2*>(base + 4 * (size_t)s * s);
   const float* go = g_out + (size_t)q * C * R * R;
-  const float Rf = (float)R;
   const int tid = threadIdx.x;
   if (s <= R) {
     build_tables(c, R, tl1, start);
@@ -528,12 +526,9 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) h[ch] = fmaf(w, vrow[ch * R + d], h[ch]);
       }
-      float ix, iy;
-      sample_pos_fast(c, j, i, Rf, ix, iy);
       float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) v[ch] = h[ch];
-      POS[(size_t)j * s + i] = make_float2(ix, iy);
       G[(size_t)j * s + i] = make_float4(v[0], v[1], v[2], v[3]);
     }
     return;
@@ -560,10 +555,153 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
         for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(wy * wx, __ldg(go + ((size_t)ch * R + y) * R + x), acc[ch]);
       }
     }
-    float ix, iy;
-    sample_pos_fast(c, j, i, Rf, ix, iy);
-    POS[(size_t)j * s + i] = make_float2(ix, iy);
     G[(size_t)j * s + i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+
+// Transposed resize, vectorised form of the kernel above (needs R % 4 == 0 and a 16-byte aligned g_out; s <= R).
+// Same band decomposition (one CTA per crop and PCL_JR intermediate rows), fewer instructions per element:
+//   tables         : rowtab[d] = (weight on i0(d), weight on i0(d)+1, i0(d)) serves both axes;
+//   vertical pass  : the band's rows are split over PCL_MG groups of two warps; a thread owns FOUR adjacent output
+//                    columns (one 16-byte load per row and channel, two rows in flight) and walks down its group's
+//                    output rows.  The partial sum a group leaves for the first row of the next group (the l1 taps of
+//                    its last run) goes to a carry buffer and is folded in after the barrier, so no row is read twice
+//                    inside a CTA (the band's own halo, 1/16 of the rows, still is);
+//   horizontal pass: a thread owns one intermediate column of FOUR intermediate rows, so window bounds, weights and loop
+//                    control are paid once per 4*C FMAs; it then writes the gradient.
+constexpr int PCL_MG = 4;
+
+template <int C, int RT>
+__global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
+                                                                 int q_base, int R_arg, float* __restrict__ ws) {
+  const int R = RT ? RT : R_arg;
+  extern __shared__ __align__(16) float sm[];
+  const int q = q_base + blockIdx.y;
+  const float* rec = params + (size_t)q * PF;
+  const Crop c = load_crop(rec);
+  const int s = c.s;
+  const int j0 = blockIdx.x * PCL_JR;
+  if (j0 >= s || s > R) return;
+  const int j1 = min(j0 + PCL_JR, s) - 1;
+  const int nx4 = R >> 2;
+  float4* rowtab = reinterpret_cast<float4*>(sm);            // [R]
+  int* start = reinterpret_cast<int*>(sm + 4 * R);           // [R+1] (padded to R+4)
+  float* Vb = sm + 5 * R + 4;                                // [PCL_JR][C][R]
+  float4* Vb4 = reinterpret_cast<float4*>(Vb);
+  float4* Cb4 = reinterpret_cast<float4*>(Vb + PCL_JR * C * R);   // [PCL_MG-1][C][R/4]
+  float* base = ws + __float_as_int(__ldg(rec + 21));
+  float4* G = reinterpret_cast<float4*>(base);
+  const float4* go4 = reinterpret_cast<const float4*>(g_out + (size_t)q * C * R * R);
+  const int tid = threadIdx.x;
+  // tables
+  for (int m = tid; m <= s; m += PCL_MT) start[m] = R;
+  __syncthreads();
+  for (int d = tid; d < R; d += PCL_MT) {
+    int i0, i1, p0 = -1, p1;
+    float l0, l1, q0, q1;
+    resize_coef(c, d, R, i0, i1, l0, l1);
+    if (d > 0) resize_coef(c, d - 1, R, p0, p1, q0, q1);
+    const bool last = i0 >= s - 1;   // the upper tap is clamped onto the same row/column: one tap of weight l0 + l1 = 1
+    rowtab[d] = make_float4(last ? 1.0f : l0, last ? 0.0f : l1, __int_as_float(i0), 0.0f);
+    for (int m = p0 + 1; m <= i0; ++m) start[m] = d;
+  }
+  __syncthreads();
+  // vertical pass
+  const int nrows = j1 - j0 + 1;
+  const int rpg = (nrows + PCL_MG - 1) / PCL_MG;
+  {
+    const int g = tid >> 6, tx = tid & 63;   // PCL_MT / PCL_MG == 64 threads per group
+    const int jA = j0 + g * rpg, jB = min(jA + rpg, j1 + 1);
+    const int plane4 = R * nx4;
+    if (jA < jB) {
+      for (int x4 = tx; x4 < nx4; x4 += 64) {
+        float4 cur[C], nxt[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) { cur[ch] = make_float4(0.f, 0.f, 0.f, 0.f); nxt[ch] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        int jc = (g == 0 && j0 > 0) ? j0 - 1 : jA;   // the band's halo: the run of row j0-1 feeds row j0 through its l1 taps
+        auto finish_row = [&](int j) {
+          if (j >= j0) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) Vb4[((j - j0) * C + ch) * nx4 + x4] = cur[ch];
+          }
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) { cur[ch] = nxt[ch]; nxt[ch] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        };
+        const int ylo = start[jc], yhi = start[jB];
+        const float4* gp = go4 + (size_t)ylo * nx4 + x4;
+        for (int y = ylo; y < yhi; y += 2, gp += 2 * nx4) {
+          float4 gv[2][C];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) gv[u][ch] = (y + u < yhi) ? __ldcs(gp + u * nx4 + ch * plane4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (y + u < yhi) {
+              const float4 T = rowtab[y + u];
+              const int i0 = __float_as_int(T.z);
+              while (i0 > jc) { finish_row(jc); ++jc; }   // group-uniform (groups are whole warps)
+#pragma unroll
+              for (int ch = 0; ch < C; ++ch) {
+                cur[ch].x = fmaf(T.x, gv[u][ch].x, cur[ch].x); cur[ch].y = fmaf(T.x, gv[u][ch].y, cur[ch].y);
+                cur[ch].z = fmaf(T.x, gv[u][ch].z, cur[ch].z); cur[ch].w = fmaf(T.x, gv[u][ch].w, cur[ch].w);
+                nxt[ch].x = fmaf(T.y, gv[u][ch].x, nxt[ch].x); nxt[ch].y = fmaf(T.y, gv[u][ch].y, nxt[ch].y);
+                nxt[ch].z = fmaf(T.y, gv[u][ch].z, nxt[ch].z); nxt[ch].w = fmaf(T.y, gv[u][ch].w, nxt[ch].w);
+              }
+            }
+          }
+        }
+        while (jc < jB) { finish_row(jc); ++jc; }   // flush (also rows whose own run is empty)
+        if (g < PCL_MG - 1 && jB <= j1) {           // what is left in `cur` belongs to the next group's first row
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) Cb4[(g * C + ch) * nx4 + x4] = cur[ch];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (PCL_MG - 1) * C * nx4; idx += PCL_MT) {
+    const int gg = idx / (C * nx4), rem = idx - gg * (C * nx4);
+    const int row = (gg + 1) * rpg;
+    if (row < nrows) {
+      float4 a = Vb4[row * C * nx4 + rem];
+      const float4 b = Cb4[idx];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      Vb4[row * C * nx4 + rem] = a;
+    }
+  }
+  __syncthreads();
+  // horizontal pass
+  const int nq = (nrows + 3) >> 2;
+  const float inv_s = 1.0f / (float)s;
+  for (int idx = tid; idx < nq * s; idx += PCL_MT) {
+    const int rq = fast_div(idx, s, inv_s), i = idx - rq * s;
+    const int wa = start[i], we = start[i + 1], wb = i > 0 ? start[i - 1] : wa;
+    const float* v0 = Vb + (size_t)(rq * 4) * C * R;
+    float h[4][C];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) h[r][ch] = 0.f;
+    for (int d = wb; d < we; ++d) {
+      const float2 T = *reinterpret_cast<const float2*>(rowtab + d);
+      const float w = d < wa ? T.y : T.x;   // run(i-1) reaches column i through its l1 taps, run(i) through its l0 taps
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) h[r][ch] = fmaf(w, v0[(r * C + ch) * R + d], h[r][ch]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = j0 + rq * 4 + r;
+      if (j <= j1) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) o[ch] = h[r][ch];
+        G[(size_t)j * s + i] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
 }
 
@@ -589,6 +727,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   float2* ent_p = reinterpret_cast<float2*>(img_sm + PCL_REG * 16);                    // [PCL_REG] ... and sample position
   int* cnt = reinterpret_cast<int*>(img_sm + PCL_REG * 24);                            // [cells]
   unsigned short* lst = reinterpret_cast<unsigned short*>(img_sm + PCL_REG * 24 + PCL_CELLS * PCL_CELLS * 4);  // [cells][K] region-local indices
+  float* tu = reinterpret_cast<float*>(img_sm + PCL_REG * 24 + PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K));             // [64] linspace of the region's columns
+  float* tv = tu + 64;                                                                                              // [64] ... and rows
   __shared__ int overflow;
   __shared__ int box[4];
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
@@ -610,7 +750,6 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     if (s > R) continue;   // outside the supported domain of the backward (see hb_pcl_bwd in the header)
     const float* base = ws + __float_as_int(__ldg(rec + 21));
     const float4* G = reinterpret_cast<const float4*>(base);
-    const float2* POS = reinterpret_cast<const float2*>(base + 4 * (size_t)s * s);
     __syncthreads();  // previous crop's readers are done with cnt/lst/ent and the region box
     if (threadIdx.x < 32) {
       // 1. (warp 0) region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
@@ -651,21 +790,40 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     const int ri0 = box[0], ri1 = box[1], rj0 = box[2], rj1 = box[3];
     if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
     const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
+    const Crop c = load_crop(rec);
+    float P[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) P[e] = c.P[e];
+    if (rw <= 64 && rh <= 64) {
+      if (threadIdx.x < rw) tu[threadIdx.x] = lin01(c, ri0 + (int)threadIdx.x);
+      else if (threadIdx.x >= 64 && threadIdx.x < 64 + rh) tv[threadIdx.x - 64] = lin01(c, rj0 + (int)threadIdx.x - 64);
+    }
+    __syncthreads();
     // 2. binning
     {
       const float inv_rw = 1.0f / (float)rw;
       const float cx_lo = (float)(tx0 - 1), cy_lo = (float)(ty0 - 1);
-      if (rw * rh > PCL_REG) {
+      if (rw * rh > PCL_REG || rw > 64 || rh > 64) {
         if (threadIdx.x == 0) overflow = 1;   // region too large to stage (extreme foreshortening): scan fallback
       } else {
-        // stage the region with cp.async (all of a thread's loads in flight at once, no register staging) ...
+        // stage the region's gradients with cp.async (all of a thread's loads in flight at once, no register staging);
+        // the sample positions are recomputed (they are not stored in the workspace)
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
           const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
           const int gidx = (rj0 + rr) * s + (ri0 + cc);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(ent_p + idx)), "l"(POS + gidx) : "memory");
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ent_g + idx)), "l"(G + gidx) : "memory");
         }
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
+          const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
+          const float u = tu[cc], v = tv[rr];
+          const float X = fmaf(P[1], v, P[0] * u) + P[2];
+          const float Y = fmaf(P[4], v, P[3] * u) + P[5];
+          const float Z = fmaf(P[7], v, P[6] * u) + P[8];
+          const float iz = __frcp_rn(1e-8f + Z);
+          ent_p[idx] = make_float2(X * iz - 0.5f, Y * iz - 0.5f);   // same expression as sample_pos_fast
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         // ... then bin this thread's own entries (it waited for its own copies; no barrier needed yet)
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
           const float2 p = ent_p[idx];
@@ -739,7 +897,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
           const float fsy = (float)sy;
           for (int j = rj0; j <= rj1; ++j)
             for (int i = ri0; i <= ri1; ++i) {
-              const float2 p = __ldg(POS + (size_t)j * s + i);
+              float2 p;
+              sample_pos_fast(c, j, i, (float)R, p.x, p.y);
               const float ax = fabsf(p.x - fsx), ay = fabsf(p.y - fsy);
               if (!(ax < 1.0f && ay < 1.0f)) continue;
               const float4 g = __ldg(G + (size_t)j * s + i);
@@ -838,8 +997,15 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const int use_tma = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15u) == 0);
   auto mid_kernel = (R == 224) ? pcl_bwd_mid_kernel<C, 224> : pcl_bwd_mid_kernel<C, 0>;
   HB_CUDA(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
+  // vectorised variant: 16-byte row segments
+  const size_t smem_mid4 = sizeof(float) * ((size_t)5 * R + 4 + (size_t)(PCL_JR + PCL_MG - 1) * C * R);
+  static int want_mid4 = -1;
+  if (want_mid4 < 0) { const char* e = getenv("HB_PCL_MID4"); want_mid4 = (e && e[0] == '0') ? 0 : 1; }
+  const bool mid4 = want_mid4 && use_tma && smem_mid4 <= 200 * 1024;
+  auto mid4_kernel = (R == 224) ? pcl_bwd_mid4_kernel<C, 224> : pcl_bwd_mid4_kernel<C, 0>;
+  if (mid4) HB_CUDA(cudaFuncSetAttribute(mid4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid4));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
-  const size_t smem_img = (size_t)PCL_REG * 24 + (size_t)PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K);
+  const size_t smem_img = (size_t)PCL_REG * 24 + (size_t)PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K) + 128 * sizeof(float);
   auto img_kernel = (R == 224) ? pcl_bwd_img_kernel<C, 224> : pcl_bwd_img_kernel<C, 0>;
   HB_CUDA(cudaFuncSetAttribute(img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
   for (int ch = 0; ch < n_chunks; ++ch) {
@@ -847,7 +1013,8 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
     dim3 g1((R + PCL_JR - 1) / PCL_JR, nim * crops_per_img);
     if (stages & 1) {
-      mid_kernel<<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
+      if (mid4) mid4_kernel<<<g1, PCL_MT, smem_mid4, st>>>(g_out, params, im0 * crops_per_img, R, ws);
+      else mid_kernel<<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
       g_launches++;
       rc = check_launch("pcl_bwd_mid_kernel");
       if (rc) return rc;
