@@ -33,6 +33,8 @@ SYMBOLS = {
     ),
     "hb_matrix_to_axis_angle_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "hb_matrix_to_axis_angle_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_rot6d_to_rotmat_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "hb_rot6d_to_rotmat_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "hb_project2d_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "hb_project2d_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "hb_weak_to_persp_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
@@ -48,6 +50,9 @@ SYMBOLS = {
 }
 
 PCL_PARAM_FLOATS = 32
+POSE_AXIS_ANGLE, POSE_ROTMAT, POSE_ROT6D = 0, 1, 2
+ROT6D_ROWS, ROT6D_COLS, ROT6D_COLS_PAIRED = 0, 1, 2
+ROT6D_LAYOUTS = {"rows": ROT6D_ROWS, "cols": ROT6D_COLS, "cols_paired": ROT6D_COLS_PAIRED}
 
 
 def lib_path():

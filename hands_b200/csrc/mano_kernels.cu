@@ -47,6 +47,7 @@ __host__ __device__ inline size_t ws_tc_end(int B, int backward) {
 struct JointState {
   float M[9];      // input rotation (after pre_rot), rotmat mode only
   float Min[9];    // raw input rotation (before pre_rot), joint 0 only
+  Rot6dCtx r6;     // 6D input modes only
   LogMapCtx lm;
   float r[3];      // full_pose = aa + pose_mean
   RodCtx rod;
@@ -61,7 +62,7 @@ struct JointState {
 };
 
 struct PoseArgs {
-  const float* pose; int is_rotmat; const float* pre_rot; const float* betas;
+  const float* pose; int fmt; const float* pre_rot; const float* betas;   // fmt: 0 axis-angle, 1 rotmat, 2+L 6D layout L
   const float* cam; const float* K; const float* transl; int B; float img_res; float min_s;
   float* fh; float* fl;   // tensor-core feature slabs (hi / lo TF32 parts) or NULL
 };
@@ -70,10 +71,17 @@ __device__ __forceinline__ float shfl16(float v, int src) { return __shfl_sync(0
 
 __device__ __forceinline__ void pose_forward(const ManoConst& c, const PoseArgs& a, int b, int i, JointState& s) {
   float aa[3];
-  if (a.is_rotmat) {
-    const float* m = a.pose + ((size_t)b * NJ + i) * 9;
+  if (a.fmt) {
+    if (a.fmt == 1) {
+      const float* m = a.pose + ((size_t)b * NJ + i) * 9;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s.M[k] = __ldg(m + k);
+      for (int k = 0; k < 9; ++k) s.M[k] = __ldg(m + k);
+    } else {
+      float x6[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) x6[k] = __ldg(a.pose + ((size_t)b * NJ + i) * 6 + k);
+      rot6d_fwd(x6, a.fmt - 2, s.M, s.r6);
+    }
     if (i == 0 && a.pre_rot) {
       float P[9];
 #pragma unroll
@@ -717,7 +725,7 @@ __global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArg
     sj1[k] = a1; sj2[k] = a2;
   }
   if (!live) return;
-  if (a.is_rotmat) {
+  if (a.fmt) {
     float gM[9];
     logmap_bwd(s.lm, g_r, gM);
     if (i == 0 && a.pre_rot) {
@@ -735,8 +743,15 @@ __global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArg
 #pragma unroll
       for (int k = 0; k < 9; ++k) gM[k] = gMin[k];
     }
+    if (a.fmt == 1) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) o.g_pose[((size_t)b * NJ + i) * 9 + k] = gM[k];
+      for (int k = 0; k < 9; ++k) o.g_pose[((size_t)b * NJ + i) * 9 + k] = gM[k];
+    } else {
+      float g6[6];
+      rot6d_bwd(s.r6, a.fmt - 2, gM, g6);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) o.g_pose[((size_t)b * NJ + i) * 6 + k] = g6[k];
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < 3; ++k) o.g_pose[(size_t)b * 48 + i * 3 + k] = g_r[k];
@@ -788,6 +803,31 @@ __global__ void logmap_bwd_kernel(const float* __restrict__ R, const float* __re
   logmap_bwd(ctx, ga, gm);
 #pragma unroll
   for (int k = 0; k < 9; ++k) g_R[(size_t)n * 9 + k] = gm[k];
+}
+__global__ void rot6d_fwd_kernel(const float* __restrict__ x6, int N, int layout, float* __restrict__ R) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float x[6], m[9];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x[k] = __ldg(x6 + (size_t)n * 6 + k);
+  Rot6dCtx ctx;
+  rot6d_fwd(x, layout, m, ctx);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[(size_t)n * 9 + k] = m[k];
+}
+__global__ void rot6d_bwd_kernel(const float* __restrict__ x6, const float* __restrict__ g_R, int N, int layout, float* __restrict__ g_x6) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float x[6], m[9], gm[9], gx[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x[k] = __ldg(x6 + (size_t)n * 6 + k);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) gm[k] = __ldg(g_R + (size_t)n * 9 + k);
+  Rot6dCtx ctx;
+  rot6d_fwd(x, layout, m, ctx);
+  rot6d_bwd(ctx, layout, gm, gx);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) g_x6[(size_t)n * 6 + k] = gx[k];
 }
 __global__ void project_fwd_kernel(const float* __restrict__ K, const float* __restrict__ pts, int B, int N, float img_res, float* __restrict__ out) {
   const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -877,7 +917,7 @@ static const size_t kSkinFwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + HBF *
 static const size_t kSkinBwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + 2 * HSUB * XS + VPB * 3 * HSUB + HSUB * 8);
 static const size_t kSkinBwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + 2 * HSUB * XS + HSUB * 8);
 
-extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot, const float* betas,
+extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
                                 const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
                                 float* vertices, float* v3d_cam, float* joints3d, float* j3d_cam, float* j2d_norm, float* cam_t,
                                 void* workspace, size_t workspace_bytes, void* stream) {
@@ -885,7 +925,8 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is
   if (rc) return rc;
   if (B == 0) return 0;
   if (!cam && (v3d_cam || j3d_cam || j2d_norm || cam_t)) { set_error("hb_mano_head_fwd: camera outputs requested without cam/K"); return HB_E_ARG; }
-  if (pre_rot && !pose_is_rotmat) { set_error("hb_mano_head_fwd: pre_rot needs rotation-matrix pose input"); return HB_E_ARG; }
+  if (pose_format < 0 || pose_format > HB_POSE_ROT6D + HB_ROT6D_COLS_PAIRED) { set_error("hb_mano_head_fwd: unknown pose_format %d", pose_format); return HB_E_ARG; }
+  if (pre_rot && !pose_format) { set_error("hb_mano_head_fwd: pre_rot needs rotation-matrix or 6D pose input"); return HB_E_ARG; }
   if ((vertices && !aligned8(vertices)) || (v3d_cam && !aligned8(v3d_cam))) { set_error("hb_mano_head_fwd: vertex outputs must be 8-byte aligned"); return HB_E_ALIGN; }
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
@@ -893,7 +934,7 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is
   float* fh = tc ? ws + ws_tc_base(B, 0) : nullptr;
   float* fl = tc ? fh + ws_tc_F(B) : nullptr;
   float* vpo = tc ? fl + ws_tc_F(B) : nullptr;
-  PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
+  PoseArgs a{pose, pose_format, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
   mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, joints3d, j3d_cam, j2d_norm, cam_t);
   g_launches++;
   rc = check_launch("mano_pose_fwd_kernel");
@@ -913,7 +954,7 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is
   return check_launch("mano_skin_fwd_kernel");
 }
 
-extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot, const float* betas,
+extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
                                 const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
                                 const float* g_vertices, const float* g_v3d_cam, const float* g_joints3d, const float* g_j3d_cam,
                                 const float* g_j2d_norm, const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam,
@@ -923,7 +964,8 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is
   if (B == 0) return 0;
   if (!g_pose || !g_betas) { set_error("hb_mano_head_bwd: g_pose and g_betas are required"); return HB_E_ARG; }
   if (!cam && (g_v3d_cam || g_j3d_cam || g_j2d_norm || g_cam_t)) { set_error("hb_mano_head_bwd: camera gradients given without cam/K"); return HB_E_ARG; }
-  if (pre_rot && !pose_is_rotmat) { set_error("hb_mano_head_bwd: pre_rot needs rotation-matrix pose input"); return HB_E_ARG; }
+  if (pose_format < 0 || pose_format > HB_POSE_ROT6D + HB_ROT6D_COLS_PAIRED) { set_error("hb_mano_head_bwd: unknown pose_format %d", pose_format); return HB_E_ARG; }
+  if (pre_rot && !pose_format) { set_error("hb_mano_head_bwd: pre_rot needs rotation-matrix or 6D pose input"); return HB_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   const bool tc = use_tc();
@@ -933,7 +975,7 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is
   float* gvh = tc ? vpo + ws_tc_vp(B) : nullptr;
   float* gvl = tc ? gvh + ws_tc_gv(B) : nullptr;
   float* gft = tc ? gvl + ws_tc_gv(B) : nullptr;
-  PoseArgs a{pose, pose_is_rotmat, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
+  PoseArgs a{pose, pose_format, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
   mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, nullptr, nullptr, nullptr, nullptr);
   g_launches++;
   rc = check_launch("mano_pose_fwd_kernel");
@@ -962,6 +1004,20 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is
   return check_launch("mano_pose_bwd_kernel");
 }
 
+extern "C" int hb_rot6d_to_rotmat_fwd(const float* x6, int N, int layout, float* R, void* stream) {
+  if (N < 0 || layout < 0 || layout > HB_ROT6D_COLS_PAIRED || (N > 0 && (!x6 || !R))) { set_error("hb_rot6d_to_rotmat_fwd: bad argument"); return HB_E_ARG; }
+  if (N == 0) return 0;
+  rot6d_fwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x6, N, layout, R);
+  g_launches++;
+  return check_launch("rot6d_fwd_kernel");
+}
+extern "C" int hb_rot6d_to_rotmat_bwd(const float* x6, const float* g_R, int N, int layout, float* g_x6, void* stream) {
+  if (N < 0 || layout < 0 || layout > HB_ROT6D_COLS_PAIRED || (N > 0 && (!x6 || !g_R || !g_x6))) { set_error("hb_rot6d_to_rotmat_bwd: bad argument"); return HB_E_ARG; }
+  if (N == 0) return 0;
+  rot6d_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x6, g_R, N, layout, g_x6);
+  g_launches++;
+  return check_launch("rot6d_bwd_kernel");
+}
 extern "C" int hb_matrix_to_axis_angle_fwd(const float* R, int N, float* aa, void* stream) {
   if (N < 0 || (N > 0 && (!R || !aa))) { set_error("hb_matrix_to_axis_angle_fwd: bad argument"); return HB_E_ARG; }
   if (N == 0) return 0;

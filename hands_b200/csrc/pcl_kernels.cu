@@ -570,10 +570,12 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
 //                    inside a CTA (the band's own halo, 1/16 of the rows, still is);
 //   horizontal pass: a thread owns one intermediate column of FOUR intermediate rows, so window bounds, weights and loop
 //                    control are paid once per 4*C FMAs; it then writes the gradient.
-constexpr int PCL_MG = 4;
+constexpr int PCL_MG = 4;               // row groups (two warps each)
+constexpr int PCL_M4T = 64 * PCL_MG;     // threads per CTA
+constexpr int PCL_MU = 2;               // output rows in flight per thread in the vertical pass
 
 template <int C, int RT>
-__global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
+__global__ void __launch_bounds__(PCL_M4T, 3) pcl_bwd_mid4_kernel(const float* __restrict__ g_out, const float* __restrict__ params,
                                                                  int q_base, int R_arg, float* __restrict__ ws) {
   const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) float sm[];
@@ -595,9 +597,9 @@ __global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __
   const float4* go4 = reinterpret_cast<const float4*>(g_out + (size_t)q * C * R * R);
   const int tid = threadIdx.x;
   // tables
-  for (int m = tid; m <= s; m += PCL_MT) start[m] = R;
+  for (int m = tid; m <= s; m += PCL_M4T) start[m] = R;
   __syncthreads();
-  for (int d = tid; d < R; d += PCL_MT) {
+  for (int d = tid; d < R; d += PCL_M4T) {
     int i0, i1, p0 = -1, p1;
     float l0, l1, q0, q1;
     resize_coef(c, d, R, i0, i1, l0, l1);
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __
   const int nrows = j1 - j0 + 1;
   const int rpg = (nrows + PCL_MG - 1) / PCL_MG;
   {
-    const int g = tid >> 6, tx = tid & 63;   // PCL_MT / PCL_MG == 64 threads per group
+    const int g = tid >> 6, tx = tid & 63;   // PCL_M4T / PCL_MG == 64 threads per group
     const int jA = j0 + g * rpg, jB = min(jA + rpg, j1 + 1);
     const int plane4 = R * nx4;
     if (jA < jB) {
@@ -630,14 +632,14 @@ __global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __
         };
         const int ylo = start[jc], yhi = start[jB];
         const float4* gp = go4 + (size_t)ylo * nx4 + x4;
-        for (int y = ylo; y < yhi; y += 2, gp += 2 * nx4) {
-          float4 gv[2][C];
+        for (int y = ylo; y < yhi; y += PCL_MU, gp += PCL_MU * nx4) {
+          float4 gv[PCL_MU][C];
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < PCL_MU; ++u)
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) gv[u][ch] = (y + u < yhi) ? __ldcs(gp + u * nx4 + ch * plane4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < PCL_MU; ++u) {
             if (y + u < yhi) {
               const float4 T = rowtab[y + u];
               const int i0 = __float_as_int(T.z);
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < (PCL_MG - 1) * C * nx4; idx += PCL_MT) {
+  for (int idx = tid; idx < (PCL_MG - 1) * C * nx4; idx += PCL_M4T) {
     const int gg = idx / (C * nx4), rem = idx - gg * (C * nx4);
     const int row = (gg + 1) * rpg;
     if (row < nrows) {
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(PCL_MT, 3) pcl_bwd_mid4_kernel(const float* __
   // horizontal pass
   const int nq = (nrows + 3) >> 2;
   const float inv_s = 1.0f / (float)s;
-  for (int idx = tid; idx < nq * s; idx += PCL_MT) {
+  for (int idx = tid; idx < nq * s; idx += PCL_M4T) {
     const int rq = fast_div(idx, s, inv_s), i = idx - rq * s;
     const int wa = start[i], we = start[i + 1], wb = i > 0 ? start[i - 1] : wa;
     const float* v0 = Vb + (size_t)(rq * 4) * C * R;
@@ -1013,7 +1015,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
     const int nim = (n_imgs - im0) < chunk_imgs ? (n_imgs - im0) : chunk_imgs;
     dim3 g1((R + PCL_JR - 1) / PCL_JR, nim * crops_per_img);
     if (stages & 1) {
-      if (mid4) mid4_kernel<<<g1, PCL_MT, smem_mid4, st>>>(g_out, params, im0 * crops_per_img, R, ws);
+      if (mid4) mid4_kernel<<<g1, PCL_M4T, smem_mid4, st>>>(g_out, params, im0 * crops_per_img, R, ws);
       else mid_kernel<<<g1, PCL_MT, smem_mid, st>>>(g_out, params, im0 * crops_per_img, R, ws, use_tma);
       g_launches++;
       rc = check_launch("pcl_bwd_mid_kernel");

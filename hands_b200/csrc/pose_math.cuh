@@ -230,4 +230,78 @@ __device__ __forceinline__ void project_bwd(const float* K, const float* X, floa
   gX[2] = K[2] * gpx + K[5] * gpy + K[8] * gpz;
 }
 
+// ---- 6D rotation representation (Zhou et al., CVPR 2019): Gram-Schmidt of two 3-vectors ---------------------------
+// The reference has three copies that differ only in memory layout (hb_rot6d_layout in the header):
+//   ROWS        pytorch3d rotation_6d_to_matrix as called at src/nets/hand_heads/hand_hmr.py:85-87:
+//               a1 = x[0:3], a2 = x[3:6], b1/b2/b3 are the ROWS of the matrix;
+//   COLS        src/models/hamer_light/geometry.py:47-62 (reshape(-1,2,3).permute(0,2,1)) and
+//               src/models/handoccnet_light/mano_head.py:132-141: a1 = x[0:3], a2 = x[3:6], b's are the COLUMNS;
+//   COLS_PAIRED common/rot.py:367-381 (reshape(-1,3,2)): a1 = x[0,2,4], a2 = x[1,3,5], b's are the COLUMNS.
+// F.normalize divides by max(||v||, 1e-12).
+struct Rot6dCtx {
+  float a2[3], b1[3], b2[3], u2[3];
+  float n1, n2, d;
+};
+
+__device__ __forceinline__ void rot6d_split(const float* x, int layout, float* a1, float* a2) {
+  if (layout == 2) { a1[0] = x[0]; a1[1] = x[2]; a1[2] = x[4]; a2[0] = x[1]; a2[1] = x[3]; a2[2] = x[5]; }
+  else { a1[0] = x[0]; a1[1] = x[1]; a1[2] = x[2]; a2[0] = x[3]; a2[1] = x[4]; a2[2] = x[5]; }
+}
+
+// x (6) -> M (3x3 row-major)
+__device__ __forceinline__ void rot6d_fwd(const float* x, int layout, float* M, Rot6dCtx& c) {
+  float a1[3];
+  rot6d_split(x, layout, a1, c.a2);
+  c.n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.b1[k] = __fdiv_rn(a1[k], c.n1);
+  c.d = c.b1[0] * c.a2[0] + c.b1[1] * c.a2[1] + c.b1[2] * c.a2[2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.u2[k] = __fsub_rn(c.a2[k], __fmul_rn(c.d, c.b1[k]));
+  c.n2 = fmaxf(sqrtf(c.u2[0] * c.u2[0] + c.u2[1] * c.u2[1] + c.u2[2] * c.u2[2]), 1e-12f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.b2[k] = __fdiv_rn(c.u2[k], c.n2);
+  float b3[3];
+  b3[0] = __fsub_rn(__fmul_rn(c.b1[1], c.b2[2]), __fmul_rn(c.b1[2], c.b2[1]));
+  b3[1] = __fsub_rn(__fmul_rn(c.b1[2], c.b2[0]), __fmul_rn(c.b1[0], c.b2[2]));
+  b3[2] = __fsub_rn(__fmul_rn(c.b1[0], c.b2[1]), __fmul_rn(c.b1[1], c.b2[0]));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (layout == 0) { M[0 * 3 + k] = c.b1[k]; M[1 * 3 + k] = c.b2[k]; M[2 * 3 + k] = b3[k]; }
+    else { M[k * 3 + 0] = c.b1[k]; M[k * 3 + 1] = c.b2[k]; M[k * 3 + 2] = b3[k]; }
+  }
+}
+
+// gM (3x3 row-major) -> g_x (6)
+__device__ __forceinline__ void rot6d_bwd(const Rot6dCtx& c, int layout, const float* gM, float* g_x) {
+  float g1[3], g2[3], g3[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (layout == 0) { g1[k] = gM[0 * 3 + k]; g2[k] = gM[1 * 3 + k]; g3[k] = gM[2 * 3 + k]; }
+    else { g1[k] = gM[k * 3 + 0]; g2[k] = gM[k * 3 + 1]; g3[k] = gM[k * 3 + 2]; }
+  }
+  // b3 = b1 x b2
+  g1[0] += c.b2[1] * g3[2] - c.b2[2] * g3[1]; g1[1] += c.b2[2] * g3[0] - c.b2[0] * g3[2]; g1[2] += c.b2[0] * g3[1] - c.b2[1] * g3[0];
+  g2[0] += g3[1] * c.b1[2] - g3[2] * c.b1[1]; g2[1] += g3[2] * c.b1[0] - g3[0] * c.b1[2]; g2[2] += g3[0] * c.b1[1] - g3[1] * c.b1[0];
+  // b2 = u2 / max(|u2|, eps)
+  float gu[3];
+  const bool clamp2 = !(c.n2 > 1e-12f);
+  const float p2 = clamp2 ? 0.0f : (c.b2[0] * g2[0] + c.b2[1] * g2[1] + c.b2[2] * g2[2]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) gu[k] = (g2[k] - c.b2[k] * p2) / c.n2;
+  // u2 = a2 - d b1,  d = b1 . a2
+  const float gd = -(c.b1[0] * gu[0] + c.b1[1] * gu[1] + c.b1[2] * gu[2]);
+  float ga2[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ga2[k] = gu[k] + gd * c.b1[k]; g1[k] += -c.d * gu[k] + gd * c.a2[k]; }
+  // b1 = a1 / max(|a1|, eps)
+  const bool clamp1 = !(c.n1 > 1e-12f);
+  const float p1 = clamp1 ? 0.0f : (c.b1[0] * g1[0] + c.b1[1] * g1[1] + c.b1[2] * g1[2]);
+  float ga1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ga1[k] = (g1[k] - c.b1[k] * p1) / c.n1;
+  if (layout == 2) { g_x[0] = ga1[0]; g_x[2] = ga1[1]; g_x[4] = ga1[2]; g_x[1] = ga2[0]; g_x[3] = ga2[1]; g_x[5] = ga2[2]; }
+  else { g_x[0] = ga1[0]; g_x[1] = ga1[1]; g_x[2] = ga1[2]; g_x[3] = ga2[0]; g_x[4] = ga2[1]; g_x[5] = ga2[2]; }
+}
+
 }  // namespace hb

@@ -77,11 +77,15 @@ class ManoHeadFunction(torch.autograd.Function):
     Reference: src/nets/hand_heads/mano_head.py:21-65 and smplx.MANO.forward."""
 
     @staticmethod
-    def forward(ctx, handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s):
+    def forward(ctx, handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s, rot6d_layout=None):
         lib = _lib.load()
         B = betas.shape[0]
-        is_rotmat = pose.dim() == 4
-        pose = _f32c(pose, "pose", (B, NJ, 3, 3) if is_rotmat else (B, 48))
+        if rot6d_layout is not None:   # (B,16,6) 6D rotations, conversion fused in front of the log map
+            is_rotmat = _lib.POSE_ROT6D + _lib.ROT6D_LAYOUTS[rot6d_layout]
+            pose = _f32c(pose, "pose", (B, NJ, 6))
+        else:
+            is_rotmat = int(pose.dim() == 4)
+            pose = _f32c(pose, "pose", (B, NJ, 3, 3) if is_rotmat else (B, 48))
         betas = _f32c(betas, "betas", (B, NB))
         cam = _f32c(cam, "cam", (B, 3))
         K = _f32c(K, "K", (B, 3, 3))
@@ -129,8 +133,34 @@ class ManoHeadFunction(torch.autograd.Function):
                                       _ptr(g_j2d), _ptr(g_cam_t), _ptr(g_pose), _ptr(g_betas), _ptr(g_cam), _ptr(g_transl), _ptr(g_pre),
                                       _ptr(ws), nbytes, _stream())
         _lib.check(rc, "hb_mano_head_bwd")
-        # inputs: handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s
-        return None, g_pose, g_betas, g_cam, None, g_transl, g_pre, None, None
+        # inputs: handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s, rot6d_layout
+        return None, g_pose, g_betas, g_cam, None, g_transl, g_pre, None, None, None
+
+
+class Rot6dToRotmatFunction(torch.autograd.Function):
+    """6D rotation representation -> rotation matrix in one of the reference's three layouts:
+    "rows" (pytorch3d rotation_6d_to_matrix, hand_hmr.py:85-87), "cols" (hamer_light/geometry.py:47-62,
+    handoccnet_light/mano_head.py:132-141), "cols_paired" (common/rot.py:367-381)."""
+
+    @staticmethod
+    def forward(ctx, x6, layout):
+        lay = _lib.ROT6D_LAYOUTS[layout]
+        x = _f32c(x6, "x6", (None, 6))
+        R = torch.empty(x.shape[0], 3, 3, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().hb_rot6d_to_rotmat_fwd(_ptr(x), x.shape[0], lay, _ptr(R), _stream()), "hb_rot6d_to_rotmat_fwd")
+        ctx.save_for_backward(x)
+        ctx.lay = lay
+        return R
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().hb_rot6d_to_rotmat_bwd(_ptr(x), _ptr(g), x.shape[0], ctx.lay, _ptr(gx), _stream()), "hb_rot6d_to_rotmat_bwd")
+        return gx, None
 
 
 class MatrixToAxisAngleFunction(torch.autograd.Function):

@@ -43,3 +43,28 @@ class MANOHead(nn.Module):
         output["beta"] = shape
         output["pose"] = rotmat_original
         return output.postfix(".r" if self.is_rhand else ".l")
+
+    def forward_rot6d(self, pose6d, shape, cam, K, layout="rows", pre_rot=None):
+        """Same outputs from the network's 6D pose read-out (B,96) / (B,16,6): the 6D -> rotation-matrix
+        conversion the reference runs just before this head (hand_hmr.py:85-87 "rows"; hamer_light/mano_head.py:98-105
+        and handoccnet_light/mano_head.py:194 "cols"; common/rot.py:367-381 "cols_paired") is fused into the pose
+        kernel.  `pose` in the result is the rotation matrices (one extra small launch), as the reference returns."""
+        from ....functional import Rot6dToRotmatFunction
+
+        B = shape.shape[0]
+        x6 = pose6d.reshape(B, 16, 6)
+        handle = self.mano.handle(shape.device)
+        vertices, v3d_cam, joints3d, j3d_cam, j2d_norm, cam_t = ManoHeadFunction.apply(
+            handle, x6, shape, cam, K, None, pre_rot, float(self.img_res), 0.1, layout
+        )
+        output = xdict()
+        output["cam_t.wp"] = cam
+        output["cam_t"] = cam_t
+        output["joints3d"] = joints3d
+        output["vertices"] = vertices
+        output["j3d.cam"] = j3d_cam
+        output["v3d.cam"] = v3d_cam
+        output["j2d.norm"] = j2d_norm
+        output["beta"] = shape
+        output["pose"] = Rot6dToRotmatFunction.apply(x6.reshape(-1, 6), layout).reshape(B, 16, 3, 3)
+        return output.postfix(".r" if self.is_rhand else ".l")

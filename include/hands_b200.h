@@ -44,6 +44,15 @@ extern "C" {
 
 typedef struct hb_mano hb_mano; /* opaque: MANO constants of one hand side on one device */
 
+/* pose input formats of hb_mano_head_fwd/bwd */
+#define HB_POSE_AXIS_ANGLE 0
+#define HB_POSE_ROTMAT 1
+#define HB_POSE_ROT6D 2 /* + hb_rot6d_layout */
+/* The reference's three 6D -> rotation-matrix conversions (Gram-Schmidt, F.normalize eps 1e-12) differ in layout: */
+#define HB_ROT6D_ROWS 0        /* pytorch3d rotation_6d_to_matrix (src/nets/hand_heads/hand_hmr.py:85-87): a1=x[0:3], a2=x[3:6], b1,b2,b3 are ROWS */
+#define HB_ROT6D_COLS 1        /* src/models/hamer_light/geometry.py:47-62, src/models/handoccnet_light/mano_head.py:132-141: a1=x[0:3], a2=x[3:6], COLUMNS */
+#define HB_ROT6D_COLS_PAIRED 2 /* common/rot.py:367-381: a1=x[0,2,4], a2=x[1,3,5], COLUMNS */
+
 const char* hb_last_error_string(void);
 int hb_version(void);
 
@@ -67,16 +76,20 @@ int hb_mano_set_tensor_core(int on);
 size_t hb_mano_workspace_bytes(int B, int backward);
 
 /* ---- MANO layer + head, forward ----------------------------------------------------------
- * Replaces: src/nets/hand_heads/mano_head.py:21-65 MANOHead.forward (pose_is_rotmat=1, cam and K
+ * Replaces: src/nets/hand_heads/mano_head.py:21-65 MANOHead.forward (pose_format=1, cam and K
  * given) and smplx.MANO.forward as called at mano_head.py:34-38, process_arctic.py:16-34,
- * src/arctic/processing.py:175-188 (pose_is_rotmat=0, cam=K=NULL, optional transl).
- *   pose      (B,16,3,3) rotation matrices if pose_is_rotmat, else (B,48) axis-angle
+ * src/arctic/processing.py:175-188 (pose_format=0, cam=K=NULL, optional transl).
+ *   pose      pose_format HB_POSE_AXIS_ANGLE: (B,48) axis-angle
+ *             pose_format HB_POSE_ROTMAT:     (B,16,3,3) rotation matrices
+ *             pose_format HB_POSE_ROT6D + L:  (B,16,6) 6D rotations in layout L (hb_rot6d_layout below): the
+ *               6D -> matrix conversion the reference runs before the head (hand_hmr.py:85-87,
+ *               hamer_light/mano_head.py:98-105, handoccnet_light/mano_head.py:194) fused in front of the log map
  *   pre_rot   (B,3,3) or NULL: left-multiplied onto joint 0 before the log map
  *             (src/models/hands_light/model.py:330-334, the PCL orientation fix-up)
  *   betas (B,10)   cam (B,3)=[s,tx,ty] or NULL   K (B,3,3) or NULL   transl (B,3) or NULL
  * Outputs (each or NULL): vertices (B,778,3), v3d_cam (B,778,3), joints3d (B,21,3),
  *   j3d_cam (B,21,3), j2d_norm (B,21,2), cam_t (B,3).  Camera outputs need cam and K. */
-int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot,
+int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot,
                      const float* betas, const float* cam, const float* K, const float* transl, int B,
                      float img_res, float min_s, float* vertices, float* v3d_cam, float* joints3d,
                      float* j3d_cam, float* j2d_norm, float* cam_t, void* workspace, size_t workspace_bytes,
@@ -86,7 +99,7 @@ int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_is_rotmat, co
  * Same inputs (saved by the caller; everything else is recomputed), upstream gradients of the
  * six outputs (each or NULL), and gradients w.r.t. pose (same shape as pose), betas, cam
  * (or NULL), transl (or NULL), pre_rot (or NULL).  K gets no gradient (data in the reference). */
-int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is_rotmat, const float* pre_rot,
+int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot,
                      const float* betas, const float* cam, const float* K, const float* transl, int B,
                      float img_res, float min_s, const float* g_vertices, const float* g_v3d_cam,
                      const float* g_joints3d, const float* g_j3d_cam, const float* g_j2d_norm,
@@ -97,6 +110,10 @@ int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_is_rotmat, co
  * common/rot.py:180-193 matrix_to_axis_angle, forward and backward; N matrices. */
 int hb_matrix_to_axis_angle_fwd(const float* R, int N, float* aa, void* stream);
 int hb_matrix_to_axis_angle_bwd(const float* R, const float* g_aa, int N, float* g_R, void* stream);
+/* 6D rotation representation -> rotation matrix, x6 (N,6) -> R (N,3,3), in one of the reference's three layouts
+ * (HB_ROT6D_* above); backward w.r.t. x6. */
+int hb_rot6d_to_rotmat_fwd(const float* x6, int N, int layout, float* R, void* stream);
+int hb_rot6d_to_rotmat_bwd(const float* x6, const float* g_R, int N, int layout, float* g_x6, void* stream);
 /* common/transforms.py:316-329 project2d_batch (+ optional data_utils.py:361-365 normalize_kp2d when
  * img_res > 0): K (B,3,3), pts (B,N,3) -> out (B,N,2); backward w.r.t. pts. */
 int hb_project2d_fwd(const float* K, const float* pts, int B, int N, float img_res, float* out, void* stream);

@@ -88,6 +88,43 @@ def matrix_to_axis_angle(m):
 
 
 # --------------------------------------------------------------------------------------
+# 6D rotation representation -> rotation matrix (three layouts in the reference)
+# --------------------------------------------------------------------------------------
+def _gram_schmidt(a1, a2):
+    b1 = F.normalize(a1, dim=-1)
+    b2 = F.normalize(a2 - torch.einsum("...i,...i->...", b1, a2).unsqueeze(-1) * b1, dim=-1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    return b1, b2, b3
+
+
+def rot6d_to_rotmat_paired(x):
+    """common/rot.py:367-381: reshape(-1,3,2); a1 = x[:, :, 0], a2 = x[:, :, 1]; b1,b2,b3 stacked as COLUMNS."""
+    x = x.reshape(-1, 3, 2)
+    return torch.stack(_gram_schmidt(x[:, :, 0], x[:, :, 1]), dim=-1)
+
+
+def rot6d_to_rotmat_cols(x):
+    """src/models/hamer_light/geometry.py:47-62: reshape(-1,2,3).permute(0,2,1).contiguous(); a1 = x[:, :, 0] (= x[0:3]),
+    a2 = x[:, :, 1] (= x[3:6]); COLUMNS.  (Same numbers as `rot6d2mat` up to the last bit: the slices are strided here.)"""
+    x = x.reshape(-1, 2, 3).permute(0, 2, 1).contiguous()
+    return torch.stack(_gram_schmidt(x[:, :, 0], x[:, :, 1]), dim=-1)
+
+
+def rot6d2mat(x):
+    """src/models/handoccnet_light/mano_head.py:132-141: a1 = x[:, 0:3], a2 = x[:, 3:6]; COLUMNS."""
+    x = x.reshape(-1, 6)
+    return torch.stack(_gram_schmidt(x[:, 0:3], x[:, 3:6]), dim=-1)
+
+
+def rotation_6d_to_matrix(d6):
+    """pytorch3d.transforms.rotation_6d_to_matrix, called at src/nets/hand_heads/hand_hmr.py:85-87.  pytorch3d is a
+    third-party dependency absent here (no version pinned by the reference): restated from its published algorithm
+    (a1 = d6[..., :3], a2 = d6[..., 3:], Gram-Schmidt, b1,b2,b3 stacked as ROWS); numerically the transpose of
+    `rot6d2mat`, which IS pinned by a golden fixture."""
+    return torch.stack(_gram_schmidt(d6[..., :3], d6[..., 3:]), dim=-2)
+
+
+# --------------------------------------------------------------------------------------
 # smplx MANO forward  [smplx-recalled; SURVEY.md Appendix A steps 1-9]
 # --------------------------------------------------------------------------------------
 def batch_rodrigues(rot_vecs):

@@ -60,6 +60,38 @@ def golden_logmap():
     )
 
 
+def golden_rot6d():
+    """The reference's three 6D -> rotation-matrix conversions.  common/rot.py, hamer_light/geometry.py and
+    handoccnet_light/mano_head.py import and run here; pytorch3d (hand_hmr.py:85-87) is absent, so its variant has no
+    fixture of its own (it is the transpose of the column-stacked one)."""
+    import importlib.util
+
+    def load(path, name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, path))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    hamer_geometry = load("src/models/hamer_light/geometry.py", "ref_hamer_geometry")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(64, 6, generator=g)
+    x[48:56] *= 1e-3        # tiny vectors
+    x[56:60, 3:] = x[56:60, :3] * 1.5 + 1e-3 * torch.randn(4, 3, generator=g)   # nearly parallel (contiguous layout)
+    out = {"x": x.numpy()}
+    for name, fn in (("paired", ref_rot.rot6d_to_rotmat), ("cols", hamer_geometry.rot6d_to_rotmat)):
+        xi = x.clone().requires_grad_(True)
+        R = fn(xi)
+        w = torch.randn(R.shape, generator=g)
+        (gx,) = torch.autograd.grad((R * w).sum(), xi)
+        out.update({f"R_{name}": R.detach().numpy(), f"w_{name}": w.numpy(), f"gx_{name}": gx.numpy()})
+    try:
+        occ = load("src/models/handoccnet_light/mano_head.py", "ref_handoccnet_mano_head")
+        out["R_handoccnet"] = occ.rot6d2mat(x).numpy()
+    except Exception as e:  # noqa: BLE001  (module-level imports of that file may be missing here)
+        print("handoccnet rot6d2mat not importable:", type(e).__name__, e)
+    np.savez_compressed(os.path.join(HERE, "rot6d.npz"), **out)
+
+
 def golden_camera_projection():
     B = 32
     rotmat, betas, cam, K = synthetic_head_inputs(B, seed=3, small_s_frac=0.25)
@@ -154,6 +186,7 @@ if __name__ == "__main__":
     golden_logmap()
     golden_camera_projection()
     golden_pcl()
+    golden_rot6d()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -104,6 +104,65 @@ def test_head_backward(heads, dev, B, is_rhand, edge, keys):
     assert (got[2].cpu()[small, 0] == 0).all()
 
 
+@pytest.mark.parametrize("layout,ofn,gkey", [("cols_paired", O.rot6d_to_rotmat_paired, "paired"), ("cols", O.rot6d_to_rotmat_cols, "cols"), ("rows", O.rotation_6d_to_matrix, None)])
+def test_rot6d_free_functions(dev, golden_dir, layout, ofn, gkey):
+    """6D -> rotation matrix, the reference's three layouts, forward and backward, against the reference's own
+    outputs (golden) and the oracle."""
+    from hands_b200.common import rot
+
+    fn = {"cols_paired": rot.rot6d_to_rotmat, "cols": rot.rot6d_to_rotmat_hamer, "rows": rot.rotation_6d_to_matrix}[layout]
+    d = np.load(os.path.join(golden_dir, "rot6d.npz"))
+    x = torch.from_numpy(d["x"])
+    g = torch.Generator().manual_seed(3)
+    w = torch.from_numpy(d[f"w_{gkey}"]) if gkey else torch.randn(64, 3, 3, generator=g)
+    xi = x.to(dev).requires_grad_(True)
+    R = fn(xi)
+    (gx,) = torch.autograd.grad((R * w.to(dev)).sum(), xi)
+    xo = x.double().requires_grad_(True)
+    Ro = ofn(xo)
+    (gxo,) = torch.autograd.grad((Ro * w.double()).sum(), xo)
+    well = slice(0, 56)   # rows 56..59 are nearly parallel pairs in the contiguous layouts: fp32 itself is ill-conditioned there
+    own = rel(ofn(x), Ro.detach())   # the fp32 reference's own distance from fp64
+    assert R.shape == (64, 3, 3) and rel(R[well], Ro.detach()[well]) <= 1e-5 and rel(R, Ro.detach()) <= max(1e-5, 3 * own)
+    assert rel(gx[well], gxo[well]) <= 1e-4
+    if gkey:
+        assert rel(R[well], torch.from_numpy(d[f"R_{gkey}"])[well]) <= 1e-6
+        assert rel(gx[well], torch.from_numpy(d[f"gx_{gkey}"])[well]) <= 1e-4
+    z = fn(torch.zeros(2, 6, device=dev))   # F.normalize eps: zero input gives the zero matrix, not NaN
+    assert torch.isfinite(z).all() and float(z.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("layout,ofn", [("rows", O.rotation_6d_to_matrix), ("cols", O.rot6d_to_rotmat_cols), ("cols_paired", O.rot6d_to_rotmat_paired)])
+def test_head_from_rot6d(heads, dev, layout, ofn):
+    """The 6D prologue fused into the head: outputs and gradients equal the reference's chain
+    rot6d -> MANOHead."""
+    B = 24
+    _, betas, cam, K = synthetic_head_inputs(B, seed=5, small_s_frac=0.2)
+    g = torch.Generator().manual_seed(9)
+    x6 = torch.randn(B, 96, generator=g)
+    keys = ("v3d.cam", "j3d.cam", "j2d.norm")
+    weights = {"v3d.cam": torch.randn(B, 778, 3, generator=g), "j3d.cam": torch.randn(B, 21, 3, generator=g), "j2d.norm": torch.randn(B, 21, 2, generator=g)}
+    xi, bi, ci = x6.to(dev).requires_grad_(True), betas.to(dev).requires_grad_(True), cam.to(dev).requires_grad_(True)
+    out = heads[True].forward_rot6d(xi, bi, ci, K.to(dev), layout=layout)
+    loss = sum((out[k + ".r"] * weights[k].to(dev)).sum() for k in keys)
+    got = torch.autograd.grad(loss, (xi, bi, ci))
+
+    def chain(dtype):
+        xo, bo, co = x6.to(dtype).requires_grad_(True), betas.to(dtype).requires_grad_(True), cam.to(dtype).requires_grad_(True)
+        rotmat = ofn(xo.reshape(-1, 6)).reshape(B, 16, 3, 3)
+        o = oracle_head(True, rotmat, bo, co, K, dtype)
+        lo = sum((o[k] * weights[k].to(dtype)).sum() for k in keys)
+        return o, rotmat, torch.autograd.grad(lo, (xo, bo, co))
+
+    o64, rot64, g64 = chain(torch.float64)
+    o32, _, g32 = chain(torch.float32)
+    for k in ("vertices", "joints3d", "v3d.cam", "j3d.cam"):
+        assert rel(out[k + ".r"], o64[k]) <= max(1e-5, 3 * rel(o32[k], o64[k])), k
+    assert rel(out["pose.r"], rot64.detach()) <= 1e-5
+    for name, a, r64, r32 in zip(("x6", "betas", "cam"), got, g64, g32):
+        assert rel(a, r64) <= max(1e-4, 3 * rel(r32, r64)), name
+
+
 @pytest.mark.parametrize("B", [8, 300])
 def test_tensor_core_and_ffma_engines_agree(heads, dev, B):
     """The blendshape contraction runs on tcgen05/TMEM (3xTF32) by default; the register-tiled FFMA engine stays

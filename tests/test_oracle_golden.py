@@ -78,3 +78,23 @@ def test_pcl_full_matches_reference(golden_dir):
                 assert np.array_equal(R[0].numpy(), g["full_rot"][j])
     finally:
         torch.set_num_threads(nt)
+
+
+def test_rot6d_matches_reference(golden_dir):
+    """The three 6D -> rotation-matrix conversions against the reference's own outputs (common/rot.py:367-381,
+    hamer_light/geometry.py:47-62, handoccnet_light/mano_head.py:132-141)."""
+    d = np.load(os.path.join(golden_dir, "rot6d.npz"))
+    x = torch.from_numpy(d["x"])
+    for name, fn in (("paired", O.rot6d_to_rotmat_paired), ("cols", O.rot6d_to_rotmat_cols)):
+        xi = x.clone().requires_grad_(True)
+        R = fn(xi)
+        assert torch.equal(R.detach(), torch.from_numpy(d[f"R_{name}"]))
+        (gx,) = torch.autograd.grad((R * torch.from_numpy(d[f"w_{name}"])).sum(), xi)
+        ref = torch.from_numpy(d[f"gx_{name}"])
+        assert float((gx - ref).abs().max() / ref.abs().max()) <= 1e-6
+    assert torch.equal(O.rot6d2mat(x), torch.from_numpy(d["R_handoccnet"]))
+    # the pytorch3d variant (absent here) is the row-stacked form of the same Gram-Schmidt
+    assert torch.equal(O.rotation_6d_to_matrix(x), O.rot6d2mat(x).transpose(1, 2))
+    Rm = O.rotation_6d_to_matrix(x[:48].double())
+    eye = torch.eye(3, dtype=torch.float64).expand_as(Rm)
+    assert float((Rm @ Rm.transpose(1, 2) - eye).abs().max()) < 1e-12 and float((torch.linalg.det(Rm) - 1).abs().max()) < 1e-12
