@@ -1,0 +1,188 @@
+// Key-point loss and metric partial sums on the head's outputs, one hand side per call.
+//   loss terms   : src/callbacks/loss/loss_arctic_sf.py:70-92,131-136 with src/utils/loss_modules.py:62-73,88-125
+//                  (hand_kp3d_loss = root-relative MSE, joints_loss = MSE, both masked by joints_valid and gated per sample,
+//                  reduced with .mean() over all B*21*D elements);
+//   metrics      : common/metrics.py:23-45 as consumed by src/utils/eval_modules.py:95-118,407-421 (root-relative per-joint
+//                  L2 averaged per hand, pixel L2 per joint after data_utils.unormalize_kp2d), and :47-55 (MRRPE).
+// One warp per hand, lane = joint; per-hand partial sums land in a (B, 8) scratch and are folded by a fixed-order
+// single-block reduction, so the sums are bit-reproducible and can be added straight into the packed all-reduce buffer.
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int KS = HB_KP_SUMS;           // 8
+
+struct KpArgs {
+  const float* j3d; const float* j2d; const float* gt3; const float* gt2; const float* jv; const float* hv; const float* gate3; const float* gate2;
+  int B; float img_res;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+__global__ void __launch_bounds__(128) kp_loss_fwd_kernel(KpArgs a, float* __restrict__ partial) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), j = threadIdx.x & 31;
+  if (b >= a.B) return;
+  const bool live = j < NOJ;
+  float d3[3] = {0.f, 0.f, 0.f}, d2[2] = {0.f, 0.f};
+  float v = 0.f;
+  if (live) {
+    const size_t o3 = ((size_t)b * NOJ + j) * 3, o2 = ((size_t)b * NOJ + j) * 2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d3[k] = __ldg(a.j3d + o3 + k) - __ldg(a.gt3 + o3 + k);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) d2[k] = __ldg(a.j2d + o2 + k) - __ldg(a.gt2 + o2 + k);
+    v = __ldg(a.jv + (size_t)b * NOJ + j);
+  }
+  // root-relative: (pred - pred_root) - (gt - gt_root) = d - d_root
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d3[k] -= __shfl_sync(0xffffffffu, d3[k], 0);
+  const float g3 = a.gate3 ? __ldg(a.gate3 + b) : 1.0f, g2 = a.gate2 ? __ldg(a.gate2 + b) : 1.0f, hv = a.hv ? __ldg(a.hv + b) : 1.0f;
+  const float sq3 = d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2], sq2 = d2[0] * d2[0] + d2[1] * d2[1];
+  const float s0 = warp_sum(live ? sq3 * v * g3 : 0.f);
+  const float s1 = warp_sum(live ? sq2 * v * g2 : 0.f);
+  const float s2 = warp_sum(live ? sqrtf(sq3) : 0.f);                                   // compute_joint3d_error: per-hand validity only
+  const float half = 0.5f * a.img_res;                                                   // unormalize_kp2d: 0.5 * img_res * (x + 1)
+  const float s4 = warp_sum(live ? sqrtf(sq2) * half * v * hv : 0.f);
+  const float s5 = warp_sum(live ? v * hv : 0.f);
+  if (j == 0) {
+    float* p = partial + (size_t)b * KS;
+    p[0] = s0; p[1] = s1; p[2] = hv * (s2 / (float)NOJ); p[3] = hv; p[4] = s4; p[5] = s5; p[6] = 0.f; p[7] = 0.f;
+  }
+}
+
+// sums[k] = sum_b partial[b][k], fixed order: thread t adds rows t, t+1024, ... then a shared-memory tree
+__global__ void __launch_bounds__(1024) kp_reduce_kernel(const float* __restrict__ partial, int B, float* __restrict__ sums) {
+  __shared__ float sh[1024];
+  for (int k = 0; k < KS; ++k) {
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += 1024) acc += partial[(size_t)b * KS + k];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int m = 512; m > 0; m >>= 1) {
+      if (threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[k] = sh[0];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) kp_loss_bwd_kernel(KpArgs a, const float* __restrict__ g_loss3, const float* __restrict__ g_loss2,
+                                                          float* __restrict__ g_j3d, float* __restrict__ g_j2d) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), j = threadIdx.x & 31;
+  if (b >= a.B) return;
+  const bool live = j < NOJ;
+  float d3[3] = {0.f, 0.f, 0.f}, d2[2] = {0.f, 0.f};
+  float v = 0.f;
+  const size_t o3 = ((size_t)b * NOJ + (live ? j : 0)) * 3, o2 = ((size_t)b * NOJ + (live ? j : 0)) * 2;
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d3[k] = __ldg(a.j3d + o3 + k) - __ldg(a.gt3 + o3 + k);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) d2[k] = __ldg(a.j2d + o2 + k) - __ldg(a.gt2 + o2 + k);
+    v = __ldg(a.jv + (size_t)b * NOJ + j);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d3[k] -= __shfl_sync(0xffffffffu, d3[k], 0);
+  const float g3 = a.gate3 ? __ldg(a.gate3 + b) : 1.0f, g2 = a.gate2 ? __ldg(a.gate2 + b) : 1.0f;
+  // loss3 = sum / (B*21*3), loss2 = sum / (B*21*2)
+  const float c3 = (g_loss3 ? __ldg(g_loss3) : 0.f) * 2.0f / ((float)a.B * (float)(NOJ * 3)) * v * g3;
+  const float c2 = (g_loss2 ? __ldg(g_loss2) : 0.f) * 2.0f / ((float)a.B * (float)(NOJ * 2)) * v * g2;
+  float gr[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { gr[k] = live ? c3 * d3[k] : 0.f; }
+  // the root joint also receives minus the sum over all joints (every joint is taken relative to it)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float tot = warp_sum(gr[k]);
+    if (j == 0) gr[k] -= tot;
+  }
+  if (live) {
+    if (g_j3d) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g_j3d[o3 + k] = gr[k];
+    }
+    if (g_j2d) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) g_j2d[o2 + k] = c2 * d2[k];
+    }
+  }
+}
+
+// MRRPE (common/metrics.py:47-55): || (root_l - root_r)_pred - (root_l - root_r)_gt ||, roots = joint 0 of (B,21,3) arrays
+__global__ void mrrpe_kernel(const float* __restrict__ pr, const float* __restrict__ pl, const float* __restrict__ gr, const float* __restrict__ gl,
+                             const float* __restrict__ valid, int B, float* __restrict__ partial) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const size_t o = (size_t)b * NOJ * 3;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float d = (__ldg(pl + o + k) - __ldg(pr + o + k)) - (__ldg(gl + o + k) - __ldg(gr + o + k));
+    sq += d * d;
+  }
+  const float v = valid ? __ldg(valid + b) : 1.0f;
+  float* p = partial + (size_t)b * KS;
+  p[0] = v * sqrtf(sq); p[1] = v;
+#pragma unroll
+  for (int k = 2; k < KS; ++k) p[k] = 0.f;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+static int kp_check(const char* what, const float* j3d, const float* j2d, const float* gt3, const float* gt2, const float* jv, int B) {
+  if (B < 0 || (B > 0 && (!j3d || !j2d || !gt3 || !gt2 || !jv))) { set_error("%s: bad argument", what); return HB_E_ARG; }
+  return 0;
+}
+
+extern "C" int hb_kp_loss_fwd(const float* j3d_cam, const float* j2d_norm, const float* gt_j3d_cam, const float* gt_j2d_norm,
+                              const float* joints_valid, const float* hand_valid, const float* gate_j3d, const float* gate_j2d, int B,
+                              float img_res, float* partial, float* sums, void* stream) {
+  int rc = kp_check("hb_kp_loss_fwd", j3d_cam, j2d_norm, gt_j3d_cam, gt_j2d_norm, joints_valid, B);
+  if (rc) return rc;
+  if (!sums || (B > 0 && !partial)) { set_error("hb_kp_loss_fwd: NULL output"); return HB_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  KpArgs a{j3d_cam, j2d_norm, gt_j3d_cam, gt_j2d_norm, joints_valid, hand_valid, gate_j3d, gate_j2d, B, img_res};
+  if (B > 0) {
+    kp_loss_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(a, partial);
+    g_launches++;
+    rc = check_launch("kp_loss_fwd_kernel");
+    if (rc) return rc;
+  }
+  kp_reduce_kernel<<<1, 1024, 0, st>>>(partial, B, sums);
+  g_launches++;
+  return check_launch("kp_reduce_kernel");
+}
+
+extern "C" int hb_kp_loss_bwd(const float* j3d_cam, const float* j2d_norm, const float* gt_j3d_cam, const float* gt_j2d_norm,
+                              const float* joints_valid, const float* gate_j3d, const float* gate_j2d, int B, const float* g_loss_kp3d,
+                              const float* g_loss_kp2d, float* g_j3d_cam, float* g_j2d_norm, void* stream) {
+  int rc = kp_check("hb_kp_loss_bwd", j3d_cam, j2d_norm, gt_j3d_cam, gt_j2d_norm, joints_valid, B);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  KpArgs a{j3d_cam, j2d_norm, gt_j3d_cam, gt_j2d_norm, joints_valid, nullptr, gate_j3d, gate_j2d, B, 0.f};
+  kp_loss_bwd_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a, g_loss_kp3d, g_loss_kp2d, g_j3d_cam, g_j2d_norm);
+  g_launches++;
+  return check_launch("kp_loss_bwd_kernel");
+}
+
+extern "C" int hb_mrrpe(const float* j3d_cam_r, const float* j3d_cam_l, const float* gt_j3d_cam_r, const float* gt_j3d_cam_l,
+                        const float* valid, int B, float* partial, float* sums, void* stream) {
+  if (B < 0 || !sums || (B > 0 && (!j3d_cam_r || !j3d_cam_l || !gt_j3d_cam_r || !gt_j3d_cam_l || !partial))) { set_error("hb_mrrpe: bad argument"); return HB_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B > 0) {
+    mrrpe_kernel<<<(B + 127) / 128, 128, 0, st>>>(j3d_cam_r, j3d_cam_l, gt_j3d_cam_r, gt_j3d_cam_l, valid, B, partial);
+    g_launches++;
+    int rc = check_launch("mrrpe_kernel");
+    if (rc) return rc;
+  }
+  kp_reduce_kernel<<<1, 1024, 0, st>>>(partial, B, sums);
+  g_launches++;
+  return check_launch("kp_reduce_kernel");
+}

@@ -129,6 +129,33 @@ int hb_persp_to_weak_fwd(const float* cam_t, const float* focal, int B, float im
 /* src/models/hands_light/model.py:330-334: out[b] = (transpose_R ? R[b]^T : R[b]) @ M[b]; N 3x3 pairs. */
 int hb_rot_apply(const float* R, const float* M, int N, int transpose_R, float* out, void* stream);
 
+/* ---- key-point losses and metric partial sums on the head's outputs -------------------------------
+ * One hand side per call.  Replaces, for the terms that read the path's outputs:
+ *   src/callbacks/loss/loss_arctic_sf.py:70-92,131-136 (hand_kp3d_loss / joints_loss of src/utils/loss_modules.py:62-73,
+ *   88-125 with MSE, masked by joints_valid (B,21), gated per sample by is_j3d_loss / is_j2d_loss (B) or NULL, .mean());
+ *   common/metrics.py:23-45 via src/utils/eval_modules.py:95-118,407-421 (root-relative MPJPE per hand, pixel error per
+ *   joint after data_utils.unormalize_kp2d) and common/metrics.py:47-55 (MRRPE).
+ * sums (HB_KP_SUMS floats, device):
+ *   [0] sum of masked/gated squared root-relative 3D errors     -> loss_kp3d = sums[0] / (B*21*3)
+ *   [1] sum of masked/gated squared normalised 2D errors        -> loss_kp2d = sums[1] / (B*21*2)
+ *   [2] sum over valid hands of mean_j ||root-relative error||,  [3] number of valid hands      (MPJPE-RA = [2]/[3])
+ *   [4] sum over valid joints of pixel L2,                       [5] number of valid joints     (pix_err  = [4]/[5])
+ * partial: (B, HB_KP_SUMS) floats of scratch.  The reduction order is fixed: bit-reproducible sums that can go straight
+ * into a packed all-reduce buffer.  hand_valid (B) or NULL (= all valid) only affects the metric sums. */
+#define HB_KP_SUMS 8
+int hb_kp_loss_fwd(const float* j3d_cam, const float* j2d_norm, const float* gt_j3d_cam, const float* gt_j2d_norm,
+                   const float* joints_valid, const float* hand_valid, const float* gate_j3d, const float* gate_j2d, int B,
+                   float img_res, float* partial, float* sums, void* stream);
+/* Gradients of (loss_kp3d, loss_kp2d) w.r.t. j3d_cam (B,21,3) and j2d_norm (B,21,2), scaled by the upstream gradients
+ * g_loss_kp3d / g_loss_kp2d (device scalars, NULL = 0); either output may be NULL. */
+int hb_kp_loss_bwd(const float* j3d_cam, const float* j2d_norm, const float* gt_j3d_cam, const float* gt_j2d_norm,
+                   const float* joints_valid, const float* gate_j3d, const float* gate_j2d, int B, const float* g_loss_kp3d,
+                   const float* g_loss_kp2d, float* g_j3d_cam, float* g_j2d_norm, void* stream);
+/* MRRPE partial sums: sums[0] = sum over valid samples of ||(root_l - root_r)_pred - (root_l - root_r)_gt||, sums[1] = count;
+ * roots are joint 0 of the (B,21,3) arrays; valid (B) or NULL. */
+int hb_mrrpe(const float* j3d_cam_r, const float* j3d_cam_l, const float* gt_j3d_cam_r, const float* gt_j3d_cam_l,
+             const float* valid, int B, float* partial, float* sums, void* stream);
+
 /* ---- Perspective Crop Layer ------------------------------------------------------------------
  * Replaces: src/datasets/hands_light_dataset.py:354-467 (per-sample CPU closure in the data loader).
  * n_crops crops; crop c samples image c / crops_per_img of `img` (n_crops/crops_per_img, C, R, R).

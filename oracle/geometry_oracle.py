@@ -252,6 +252,41 @@ def mano_head_forward(buf, rotmat, shape, cam, K, img_res=224.0, min_s=0.1):
 
 
 # --------------------------------------------------------------------------------------
+# key-point losses and metrics on the head's outputs
+# --------------------------------------------------------------------------------------
+def keypoint_losses(j3d, j2d, gt3, gt2, joints_valid, gate3=None, gate2=None):
+    """src/callbacks/loss/loss_arctic_sf.py:70-92,131-136 + src/utils/loss_modules.py:62-73 (keypoint_3d_loss),
+    :88-95 (hand_kp3d_loss), :116-125 (joints_loss): MSE, root-relative for 3D, masked by joints_valid, gated per
+    sample, reduced with .mean()."""
+    B = j3d.shape[0]
+    d3 = ((j3d - j3d[:, :1]) - (gt3 - gt3[:, :1])) ** 2 * joints_valid[:, :, None]
+    d2 = (j2d - gt2) ** 2 * joints_valid[:, :, None]
+    d3, d2 = d3.reshape(B, -1), d2.reshape(B, -1)
+    if gate3 is not None:
+        d3 = d3 * gate3[..., None]
+    if gate2 is not None:
+        d2 = d2 * gate2[..., None]
+    return d3.mean(), d2.mean()
+
+
+def keypoint_metric_sums(j3d, j2d, gt3, gt2, joints_valid, hand_valid, img_res):
+    """common/metrics.py:23-45 as called from src/utils/eval_modules.py:95-118 (root-relative, per-hand validity, mean over
+    joints) and :407-421 (pixel error on data_utils.unormalize_kp2d'ed key-points, per-joint validity x hand validity):
+    numerators and counts of the nan-means the reference takes afterwards."""
+    dist3 = (((gt3 - gt3[:, :1]) - (j3d - j3d[:, :1])) ** 2).sum(dim=2).sqrt().mean(dim=1)
+    half = 0.5 * img_res
+    dist2 = (((half * (gt2 + 1)) - (half * (j2d + 1))) ** 2).sum(dim=2).sqrt()
+    v2 = joints_valid * hand_valid[:, None]
+    return (dist3 * hand_valid).sum(), hand_valid.sum(), (dist2 * v2).sum(), v2.sum()
+
+
+def mrrpe_sums(root_r, root_l, gt_root_r, gt_root_l, valid):
+    """common/metrics.py:47-55."""
+    d = (((root_l - root_r) - (gt_root_l - gt_root_r)) ** 2).sum(dim=1).sqrt()
+    return (d * valid).sum(), valid.sum()
+
+
+# --------------------------------------------------------------------------------------
 # Perspective Crop Layer      (src/datasets/hands_light_dataset.py:354-467)
 # --------------------------------------------------------------------------------------
 def virtual_camera_rotation(p):

@@ -92,6 +92,43 @@ def golden_rot6d():
     np.savez_compressed(os.path.join(HERE, "rot6d.npz"), **out)
 
 
+def golden_kp_loss():
+    """Loss terms and metrics that read the path's outputs, from the reference's own functions
+    (src/utils/loss_modules.py, common/metrics.py, common/data_utils.py)."""
+    import src.utils.loss_modules as ref_lm
+    import common.metrics as ref_metrics
+
+    g = torch.Generator().manual_seed(21)
+    B = 37
+    j3d = (0.1 * torch.randn(B, 21, 3, generator=g) + torch.tensor([0.0, 0.0, 0.6])).requires_grad_(True)
+    gt3 = 0.1 * torch.randn(B, 21, 3, generator=g) + torch.tensor([0.0, 0.0, 0.6])
+    j2d = (0.5 * torch.randn(B, 21, 2, generator=g)).requires_grad_(True)
+    gt2 = 0.5 * torch.randn(B, 21, 2, generator=g)
+    jv = (torch.rand(B, 21, generator=g) > 0.2).float()
+    hv = (torch.rand(B, generator=g) > 0.15).float()
+    gate3 = (torch.rand(B, generator=g) > 0.3).float()
+    gate2 = (torch.rand(B, generator=g) > 0.3).float()
+    mse = torch.nn.MSELoss(reduction="none")
+    l3 = ref_lm.hand_kp3d_loss(j3d, gt3, mse, jv, return_mean=False)                 # loss_arctic_sf.py:87-92
+    l2 = ref_lm.joints_loss(j2d, gt2, criterion=mse, jts_valid=jv, return_mean=False)  # :70-83
+    l3 = (l3.reshape(B, -1) * gate3[..., None]).mean()                               # :131-136, :146-158
+    l2 = (l2.reshape(B, -1) * gate2[..., None]).mean()
+    g3, g2 = torch.autograd.grad(5.0 * l3 + 3.0 * l2, (j3d, j2d))
+    with torch.no_grad():
+        ra = lambda t: t - t[:, :1, :]  # noqa: E731  (eval_modules.py:105-108)
+        mp = ref_metrics.compute_joint3d_error(ra(gt3), ra(j3d), hv).mean(axis=1)     # eval_modules.py:111-118
+        pix = ref_metrics.compute_pixel_error(ref_data_utils.unormalize_kp2d(gt2, 224), ref_data_utils.unormalize_kp2d(j2d.detach(), 224), jv * hv.view(-1, 1))
+        j3d_l = j3d.detach() + 0.05 * torch.randn(B, 21, 3, generator=g)
+        gt3_l = gt3 + 0.05 * torch.randn(B, 21, 3, generator=g)
+        mrrpe = ref_metrics.compute_mrrpe(gt3[:, 0], gt3_l[:, 0], j3d.detach()[:, 0], j3d_l[:, 0], hv)
+    np.savez_compressed(
+        os.path.join(HERE, "kp_loss.npz"),
+        j3d=j3d.detach().numpy(), gt3=gt3.numpy(), j2d=j2d.detach().numpy(), gt2=gt2.numpy(), jv=jv.numpy(), hv=hv.numpy(),
+        gate3=gate3.numpy(), gate2=gate2.numpy(), loss3=l3.detach().numpy(), loss2=l2.detach().numpy(), g3=g3.numpy(), g2=g2.numpy(),
+        mpjpe=mp, pix=pix, j3d_l=j3d_l.numpy(), gt3_l=gt3_l.numpy(), mrrpe=mrrpe,
+    )
+
+
 def golden_camera_projection():
     B = 32
     rotmat, betas, cam, K = synthetic_head_inputs(B, seed=3, small_s_frac=0.25)
@@ -187,6 +224,7 @@ if __name__ == "__main__":
     golden_camera_projection()
     golden_pcl()
     golden_rot6d()
+    golden_kp_loss()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -163,6 +163,40 @@ def test_head_from_rot6d(heads, dev, layout, ofn):
         assert rel(a, r64) <= max(1e-4, 3 * rel(r32, r64)), name
 
 
+def test_keypoint_losses_and_metric_sums(dev, golden_dir):
+    """loss terms + metric partial sums straight from the head's outputs, against the reference's own
+    functions (golden) -- values, gradients, and the partial sums the packed all-reduce carries."""
+    from hands_b200.losses import keypoint_losses, mrrpe_sums
+
+    d = {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(os.path.join(golden_dir, "kp_loss.npz")).items()}
+    c = {k: v.to(dev) for k, v in d.items()}
+    j3d, j2d = c["j3d"].clone().requires_grad_(True), c["j2d"].clone().requires_grad_(True)
+    l3, l2, sums = keypoint_losses(j3d, j2d, c["gt3"], c["gt2"], c["jv"], c["hv"], c["gate3"], c["gate2"], img_res=224)
+    assert abs(float(l3) - float(d["loss3"])) <= 1e-5 * float(d["loss3"]) and abs(float(l2) - float(d["loss2"])) <= 1e-5 * float(d["loss2"])
+    g3, g2 = torch.autograd.grad(5.0 * l3 + 3.0 * l2, (j3d, j2d))
+    assert rel(g3, d["g3"]) <= 1e-4 and rel(g2, d["g2"]) <= 1e-4
+    s = sums.cpu().double()
+    mp, pix = d["mpjpe"].numpy(), d["pix"].numpy()
+    assert int(s[3]) == int(np.isfinite(mp).sum()) and int(s[5]) == int(np.isfinite(pix).sum())          # counts: bit-exact
+    assert abs(float(s[2] / s[3]) - float(np.nanmean(mp))) <= 1e-5 * float(np.nanmean(mp))
+    assert abs(float(s[4] / s[5]) - float(np.nanmean(pix))) <= 1e-5 * float(np.nanmean(pix))           # well inside 1e-3 px
+    m = mrrpe_sums(c["j3d"], c["j3d_l"], c["gt3"], c["gt3_l"], c["hv"]).cpu().double()
+    ref = d["mrrpe"].numpy()
+    assert int(m[1]) == int(np.isfinite(ref).sum()) and abs(float(m[0] / m[1]) - float(np.nanmean(ref))) <= 1e-5 * float(np.nanmean(ref))
+    # reproducible: the reduction order is fixed
+    _, _, sums2 = keypoint_losses(c["j3d"], c["j2d"], c["gt3"], c["gt2"], c["jv"], c["hv"], c["gate3"], c["gate2"], img_res=224)
+    assert torch.equal(sums, sums2)
+    # no gates / masks given, larger ragged batch, against the oracle
+    g = torch.Generator().manual_seed(2)
+    B = 1031
+    a3, b3 = torch.randn(B, 21, 3, generator=g), torch.randn(B, 21, 3, generator=g)
+    a2, b2 = torch.randn(B, 21, 2, generator=g), torch.randn(B, 21, 2, generator=g)
+    ones = torch.ones(B, 21)
+    l3, l2, _ = keypoint_losses(a3.to(dev), a2.to(dev), b3.to(dev), b2.to(dev), ones.to(dev))
+    o3, o2 = O.keypoint_losses(a3.double(), a2.double(), b3.double(), b2.double(), ones.double())
+    assert abs(float(l3) - float(o3)) <= 1e-5 * float(o3) and abs(float(l2) - float(o2)) <= 1e-5 * float(o2)
+
+
 @pytest.mark.parametrize("B", [8, 300])
 def test_tensor_core_and_ffma_engines_agree(heads, dev, B):
     """The blendshape contraction runs on tcgen05/TMEM (3xTF32) by default; the register-tiled FFMA engine stays

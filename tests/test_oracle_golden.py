@@ -98,3 +98,19 @@ def test_rot6d_matches_reference(golden_dir):
     Rm = O.rotation_6d_to_matrix(x[:48].double())
     eye = torch.eye(3, dtype=torch.float64).expand_as(Rm)
     assert float((Rm @ Rm.transpose(1, 2) - eye).abs().max()) < 1e-12 and float((torch.linalg.det(Rm) - 1).abs().max()) < 1e-12
+
+
+def test_keypoint_losses_and_metrics_match_reference(golden_dir):
+    """Loss terms / metrics on the path's outputs against the reference's own functions (loss_modules.py, metrics.py)."""
+    d = {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(os.path.join(golden_dir, "kp_loss.npz")).items()}
+    j3d, j2d = d["j3d"].clone().requires_grad_(True), d["j2d"].clone().requires_grad_(True)
+    l3, l2 = O.keypoint_losses(j3d, j2d, d["gt3"], d["gt2"], d["jv"], d["gate3"], d["gate2"])
+    assert abs(float(l3) - float(d["loss3"])) <= 1e-6 * float(d["loss3"]) and abs(float(l2) - float(d["loss2"])) <= 1e-6 * float(d["loss2"])
+    g3, g2 = torch.autograd.grad(5.0 * l3 + 3.0 * l2, (j3d, j2d))
+    assert float((g3 - d["g3"]).abs().max()) <= 1e-6 * float(d["g3"].abs().max()) and float((g2 - d["g2"]).abs().max()) <= 1e-6 * float(d["g2"].abs().max())
+    s2, n2, s4, n4 = O.keypoint_metric_sums(d["j3d"], d["j2d"], d["gt3"], d["gt2"], d["jv"], d["hv"], 224.0)
+    assert abs(float(s2 / n2) - float(np.nanmean(d["mpjpe"].numpy()))) <= 1e-6
+    assert abs(float(s4 / n4) - float(np.nanmean(d["pix"].numpy()))) <= 1e-4
+    assert int(n2) == int(np.isfinite(d["mpjpe"].numpy()).sum()) and int(n4) == int(np.isfinite(d["pix"].numpy()).sum())
+    sm, nm = O.mrrpe_sums(d["j3d"][:, 0], d["j3d_l"][:, 0], d["gt3"][:, 0], d["gt3_l"][:, 0], d["hv"])
+    assert abs(float(sm / nm) - float(np.nanmean(d["mrrpe"].numpy()))) <= 1e-6
