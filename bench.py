@@ -277,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
         tt = {"pcl_fwd_kernel": tk_fwd, "pcl_bwd_mid_kernel": tk_mid, "pcl_bwd_img_kernel": tk_img}
         for name in ab:
             kern[name] = {"us_per_launch": tt[name] * 1e6, "alg_bytes_per_launch": ab[name], "achieved": ab[name] / tt[name] / 1e9,
-                          "frac": ab[name] / tt[name] / 1e9 / peak, "traffic": traffic.get(name), "crops_per_launch": ks.n}
+                          "frac": ab[name] / tt[name] / 1e9 / peak, "traffic": next((v for k, v in traffic.items() if k.startswith(name[:-len("_kernel")])), None), "crops_per_launch": ks.n}
         del ks
 
     # ---- e2e: host buffers, copies inside the timed region ---------------------------------------------
