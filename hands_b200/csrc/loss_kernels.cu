@@ -132,6 +132,50 @@ __global__ void mrrpe_kernel(const float* __restrict__ pr, const float* __restri
   for (int k = 2; k < KS; ++k) p[k] = 0.f;
 }
 
+// GT-side glue of process_data_light (src/callbacks/process/process_arctic.py:42-65), one hand side:
+//   Tr0 = mean_j (j3d_full - joints_cano);  v3d_cam = vertices_cano + Tr0;  cam_t = j3d_full[:,0] - joints_cano[:,0];
+//   cam_t_wp = perspective_to_weak_perspective_torch(cam_t, (K00+K11)/2, img_res)   (common/camera.py:10-29)
+// One CTA of 128 threads per hand: warp 0 reduces the 21 joint offsets, all threads then stream the 778 vertices.
+__global__ void __launch_bounds__(128) gt_process_kernel(const float* __restrict__ joints, const float* __restrict__ verts,
+                                                         const float* __restrict__ j3d_full, const float* __restrict__ K, int B, float img_res,
+                                                         float* __restrict__ v3d_cam, float* __restrict__ cam_t, float* __restrict__ cam_t_wp) {
+  __shared__ float tr[3];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 32) {
+    const int j = threadIdx.x;
+    float d[3] = {0.f, 0.f, 0.f};
+    if (j < NOJ) {
+      const size_t o = ((size_t)b * NOJ + j) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d[k] = __ldg(j3d_full + o + k) - __ldg(joints + o + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float root = __shfl_sync(0xffffffffu, d[k], 0);
+      const float m = warp_sum(d[k]) / (float)NOJ;
+      if (j == 0) {
+        tr[k] = m;
+        if (cam_t) cam_t[(size_t)b * 3 + k] = root;
+        if (cam_t_wp && k == 2) {
+          const float f = __fdiv_rn(__fadd_rn(__ldg(K + (size_t)b * 9 + 0), __ldg(K + (size_t)b * 9 + 4)), 2.0f);
+          cam_t_wp[(size_t)b * 3 + 0] = __fdiv_rn(2.0f * f, __fadd_rn(__fmul_rn(img_res, root), 1e-9f));
+        }
+        if (cam_t_wp && k < 2) cam_t_wp[(size_t)b * 3 + 1 + k] = root;
+      }
+    }
+  }
+  __syncthreads();
+  if (v3d_cam) {
+    const float t0 = tr[0], t1 = tr[1], t2 = tr[2];
+    const float* vi = verts + (size_t)b * HB_NUM_VERTS * 3;
+    float* vo = v3d_cam + (size_t)b * HB_NUM_VERTS * 3;
+    for (int e = threadIdx.x; e < HB_NUM_VERTS * 3; e += 128) {
+      const int k = e % 3;
+      vo[e] = __ldg(vi + e) + (k == 0 ? t0 : (k == 1 ? t1 : t2));
+    }
+  }
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -185,4 +229,13 @@ extern "C" int hb_mrrpe(const float* j3d_cam_r, const float* j3d_cam_l, const fl
   kp_reduce_kernel<<<1, 1024, 0, st>>>(partial, B, sums);
   g_launches++;
   return check_launch("kp_reduce_kernel");
+}
+
+extern "C" int hb_gt_process(const float* joints3d, const float* vertices, const float* j3d_full, const float* K, int B, float img_res,
+                             float* v3d_cam, float* cam_t, float* cam_t_wp, void* stream) {
+  if (B < 0 || (B > 0 && (!joints3d || !j3d_full || (v3d_cam && !vertices) || (cam_t_wp && !K)))) { set_error("hb_gt_process: bad argument"); return HB_E_ARG; }
+  if (B == 0) return 0;
+  gt_process_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(joints3d, vertices, j3d_full, K, B, img_res, v3d_cam, cam_t, cam_t_wp);
+  g_launches++;
+  return check_launch("gt_process_kernel");
 }

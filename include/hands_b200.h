@@ -155,6 +155,13 @@ int hb_kp_loss_bwd(const float* j3d_cam, const float* j2d_norm, const float* gt_
  * roots are joint 0 of the (B,21,3) arrays; valid (B) or NULL. */
 int hb_mrrpe(const float* j3d_cam_r, const float* j3d_cam_l, const float* gt_j3d_cam_r, const float* gt_j3d_cam_l,
              const float* valid, int B, float* partial, float* sums, void* stream);
+/* GT-side glue of process_data_light (src/callbacks/process/process_arctic.py:42-65), one hand side, after the no-grad MANO
+ * forward of the ground-truth parameters (hb_mano_head_fwd with HB_POSE_AXIS_ANGLE, cam = K = NULL):
+ *   Tr0 = mean_j (j3d_full - joints3d);  v3d_cam = vertices + Tr0;  cam_t = j3d_full[:,0] - joints3d[:,0];
+ *   cam_t_wp = perspective_to_weak_perspective_torch(cam_t, (K00+K11)/2, img_res)  (common/camera.py:10-29).
+ * joints3d, j3d_full (B,21,3); vertices, v3d_cam (B,778,3); K (B,3,3); cam_t, cam_t_wp (B,3).  Outputs may be NULL. */
+int hb_gt_process(const float* joints3d, const float* vertices, const float* j3d_full, const float* K, int B, float img_res,
+                  float* v3d_cam, float* cam_t, float* cam_t_wp, void* stream);
 
 /* ---- Perspective Crop Layer ------------------------------------------------------------------
  * Replaces: src/datasets/hands_light_dataset.py:354-467 (per-sample CPU closure in the data loader).

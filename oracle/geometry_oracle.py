@@ -287,6 +287,20 @@ def mrrpe_sums(root_r, root_l, gt_root_r, gt_root_l, valid):
 
 
 # --------------------------------------------------------------------------------------
+# GT side of a step      (src/callbacks/process/process_arctic.py:4-75)
+# --------------------------------------------------------------------------------------
+def process_gt_side(buf, pose, betas, j3d_full, K, img_res):
+    """One hand side of process_data_light: canonical MANO forward of the GT parameters (:16-21), mean-offset translation
+    into camera space (:42-46), GT camera translation (:49-52) and its weak-perspective form (:58-65)."""
+    verts, joints = mano_forward(buf, betas, pose[:, :3], pose[:, 3:])
+    Tr0 = (j3d_full - joints).mean(dim=1)
+    cam_t = j3d_full[:, 0] - joints[:, 0]
+    f = (K[:, 0, 0] + K[:, 1, 1]) / 2.0
+    return {"joints3d": joints, "vertices": verts, "v3d.cam": verts + Tr0[:, None, :], "cam_t": cam_t,
+            "cam_t.wp": perspective_to_weak_perspective(cam_t, f, img_res)}
+
+
+# --------------------------------------------------------------------------------------
 # Perspective Crop Layer      (src/datasets/hands_light_dataset.py:354-467)
 # --------------------------------------------------------------------------------------
 def virtual_camera_rotation(p):

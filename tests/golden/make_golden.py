@@ -129,6 +129,47 @@ def golden_kp_loss():
     )
 
 
+def golden_process_gt():
+    """The reference's own process_data_light (src/callbacks/process/process_arctic.py:4-75), run with MANO layers that wrap
+    the oracle's smplx restatement on the seeded synthetic constants (smplx itself is absent): pins the glue arithmetic
+    (mean-offset translation, GT camera translation, weak-perspective camera) against the reference's code."""
+    import importlib.util
+    from types import SimpleNamespace
+
+    from hands_b200.synthetic import synthetic_mano_buffers
+    from oracle import geometry_oracle as O
+
+    spec = importlib.util.spec_from_file_location("ref_process_arctic", os.path.join(REF, "src/callbacks/process/process_arctic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    def layer(is_rhand):
+        buf = synthetic_mano_buffers(is_rhand)
+
+        def fwd(betas, hand_pose, global_orient, transl=None):
+            v, j = O.mano_forward(buf, betas, global_orient, hand_pose, transl)
+            return SimpleNamespace(vertices=v, joints=j)
+
+        return fwd
+
+    g = torch.Generator().manual_seed(31)
+    B = 9
+    targets = {}
+    for side in ("r", "l"):
+        targets[f"mano.pose.{side}"] = 0.3 * torch.randn(B, 48, generator=g)
+        targets[f"mano.beta.{side}"] = torch.randn(B, 10, generator=g)
+        targets[f"mano.j3d.full.{side}"] = 0.08 * torch.randn(B, 21, 3, generator=g) + torch.tensor([0.05, -0.02, 0.7])
+    f = 300 + 1200 * torch.rand(B, generator=g)
+    K = torch.zeros(B, 3, 3)
+    K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = f, f * 1.01, 112.0, 112.0, 1.0
+    inp = {k: v.clone() for k, v in targets.items()}
+    _, out, _ = mod.process_data_light({"mano_r": layer(True), "mano_l": layer(False)}, {}, targets, {"intrinsics": K}, "train", SimpleNamespace(img_res=224))
+    save = {"in_" + k: v.numpy() for k, v in inp.items()}
+    save["K"] = K.numpy()
+    save.update({"out_" + k: v.numpy() for k, v in out.items() if k not in inp})
+    np.savez_compressed(os.path.join(HERE, "process_gt.npz"), **save)
+
+
 def golden_camera_projection():
     B = 32
     rotmat, betas, cam, K = synthetic_head_inputs(B, seed=3, small_s_frac=0.25)
@@ -225,6 +266,7 @@ if __name__ == "__main__":
     golden_pcl()
     golden_rot6d()
     golden_kp_loss()
+    golden_process_gt()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -197,6 +197,28 @@ def test_keypoint_losses_and_metric_sums(dev, golden_dir):
     assert abs(float(l3) - float(o3)) <= 1e-5 * float(o3) and abs(float(l2) - float(o2)) <= 1e-5 * float(o2)
 
 
+def test_process_data_light_gt_side(dev, golden_dir):
+    """the drop-in process_data_light against the reference's own function (golden)."""
+    from types import SimpleNamespace
+
+    from hands_b200.common.body_models import build_mano_aa
+    from hands_b200.src.callbacks.process.process_arctic import process_data_light
+
+    d = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "process_gt.npz")).items()}
+    models = {"mano_r": build_mano_aa(True, synthetic=True).to(dev), "mano_l": build_mano_aa(False, synthetic=True).to(dev)}
+    targets = {k[3:]: v.to(dev) for k, v in d.items() if k.startswith("in_")}
+    _, out, _ = process_data_light(models, {}, targets, {"intrinsics": d["K"].to(dev)}, "train", SimpleNamespace(img_res=224))
+    for k, ref in d.items():
+        if not k.startswith("out_"):
+            continue
+        got = out[k[4:]]
+        assert got.shape == ref.shape, k
+        tol = 1e-5 if "wp" not in k else 2e-6
+        assert rel(got, ref) <= tol, (k, rel(got, ref))
+    assert out["mano.j3d.cam.r"] is targets["mano.j3d.full.r"]
+    assert not out["mano.v3d.cam.r"].requires_grad
+
+
 @pytest.mark.parametrize("B", [8, 300])
 def test_tensor_core_and_ffma_engines_agree(heads, dev, B):
     """The blendshape contraction runs on tcgen05/TMEM (3xTF32) by default; the register-tiled FFMA engine stays

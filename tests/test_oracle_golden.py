@@ -114,3 +114,16 @@ def test_keypoint_losses_and_metrics_match_reference(golden_dir):
     assert int(n2) == int(np.isfinite(d["mpjpe"].numpy()).sum()) and int(n4) == int(np.isfinite(d["pix"].numpy()).sum())
     sm, nm = O.mrrpe_sums(d["j3d"][:, 0], d["j3d_l"][:, 0], d["gt3"][:, 0], d["gt3_l"][:, 0], d["hv"])
     assert abs(float(sm / nm) - float(np.nanmean(d["mrrpe"].numpy()))) <= 1e-6
+
+
+def test_process_gt_matches_reference(golden_dir):
+    """GT side of a step: the oracle against the reference's own process_data_light (process_arctic.py:4-75) run on the
+    same MANO restatement -- pins the glue (mean-offset translation, GT camera translation, weak-perspective camera)."""
+    from hands_b200.synthetic import synthetic_mano_buffers
+
+    d = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "process_gt.npz")).items()}
+    for side, is_rhand in (("r", True), ("l", False)):
+        o = O.process_gt_side(synthetic_mano_buffers(is_rhand), d[f"in_mano.pose.{side}"], d[f"in_mano.beta.{side}"], d[f"in_mano.j3d.full.{side}"], d["K"], 224)
+        for key, name in (("joints3d", "joints3d"), ("vertices", "vertices"), ("v3d.cam", "v3d.cam"), ("cam_t", "cam_t"), ("cam_t.wp", "cam_t.wp")):
+            assert torch.equal(o[key], d[f"out_mano.{name}.{side}"]), (side, key)
+        assert torch.equal(d[f"out_mano.j3d.cam.{side}"], d[f"in_mano.j3d.full.{side}"])
