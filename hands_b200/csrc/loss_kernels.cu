@@ -176,6 +176,46 @@ __global__ void __launch_bounds__(128) gt_process_kernel(const float* __restrict
   }
 }
 
+// KPE features of a crop box (src/datasets/hands_light_dataset.py:259-279) and their sinusoidal encodings
+// (src/models/hands_light/model.py:444-460), batched.  Angles are computed in float64 like numpy and cast to fp32:
+//   center_angle (2)  = atan2(c - K[.,2], K[.,.]) for the box centre,  corner_angle (8) for the corners
+//   (x0,y0), (x0,y1), (x1,y0), (x1,y1);  enc[l][c][0/1] = sin / cos(2^l * angle[c]),  l < L.
+__global__ void kpe_kernel(const int32_t* __restrict__ bbox, const float* __restrict__ K, int n, int L, float* __restrict__ center_angle,
+                           float* __restrict__ corner_angle, float* __restrict__ center_enc, float* __restrict__ corner_enc) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double x0 = bbox[(size_t)q * 4 + 0], y0 = bbox[(size_t)q * 4 + 1], x1 = bbox[(size_t)q * 4 + 2], y1 = bbox[(size_t)q * 4 + 3];
+  const double fx = K[(size_t)q * 9 + 0], fy = K[(size_t)q * 9 + 4], cx = K[(size_t)q * 9 + 2], cy = K[(size_t)q * 9 + 5];
+  float ang[10];
+  ang[0] = (float)atan2((x0 + x1) / 2.0 - cx, fx);
+  ang[1] = (float)atan2((y0 + y1) / 2.0 - cy, fy);
+  const double xs[4] = {x0, x0, x1, x1}, ys[4] = {y0, y1, y0, y1};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { ang[2 + 2 * c] = (float)atan2(xs[c] - cx, fx); ang[3 + 2 * c] = (float)atan2(ys[c] - cy, fy); }
+  if (center_angle) { center_angle[(size_t)q * 2 + 0] = ang[0]; center_angle[(size_t)q * 2 + 1] = ang[1]; }
+  if (corner_angle) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) corner_angle[(size_t)q * 8 + c] = ang[2 + c];
+  }
+  float freq = 1.0f;
+  for (int l = 0; l < L; ++l, freq *= 2.0f) {
+    if (center_enc) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float a = __fmul_rn(freq, ang[c]);
+        center_enc[((size_t)q * L + l) * 4 + c * 2 + 0] = sinf(a); center_enc[((size_t)q * L + l) * 4 + c * 2 + 1] = cosf(a);
+      }
+    }
+    if (corner_enc) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float a = __fmul_rn(freq, ang[2 + c]);
+        corner_enc[((size_t)q * L + l) * 16 + c * 2 + 0] = sinf(a); corner_enc[((size_t)q * L + l) * 16 + c * 2 + 1] = cosf(a);
+      }
+    }
+  }
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -238,4 +278,13 @@ extern "C" int hb_gt_process(const float* joints3d, const float* vertices, const
   gt_process_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(joints3d, vertices, j3d_full, K, B, img_res, v3d_cam, cam_t, cam_t_wp);
   g_launches++;
   return check_launch("gt_process_kernel");
+}
+
+extern "C" int hb_kpe_features(const int32_t* bbox, const float* K, int n, int n_freq, float* center_angle, float* corner_angle,
+                               float* center_enc, float* corner_enc, void* stream) {
+  if (n < 0 || n_freq < 0 || n_freq > 30 || (n > 0 && (!bbox || !K))) { set_error("hb_kpe_features: bad argument"); return HB_E_ARG; }
+  if (n == 0) return 0;
+  kpe_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bbox, K, n, n_freq, center_angle, corner_angle, center_enc, corner_enc);
+  g_launches++;
+  return check_launch("kpe_kernel");
 }

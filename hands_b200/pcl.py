@@ -21,3 +21,27 @@ def apply_virtual_rotation(R_virt2orig, pose):
     (src/models/hands_light/model.py:330-334, written out-of-place so autograd stays valid)."""
     rotated = RotApplyFunction.apply(R_virt2orig, pose[:, 0])
     return torch.cat([rotated[:, None], pose[:, 1:]], dim=1)
+
+
+def kpe_features(bbox_xyxy, K, n_freq):
+    """KPE angles of the crop boxes and their sinusoidal encodings, batched on the GPU (the reference computes the angles per
+    sample on the CPU, src/datasets/hands_light_dataset.py:259-279, and the encodings in the model,
+    src/models/hands_light/model.py:444-460).  bbox_xyxy (n,4) int, K (n,3,3) ->
+    dict(center_angle (n,2), corner_angle (n,8), center_pos_enc (n, n_freq*4), corner_pos_enc (n, n_freq*16))."""
+    import torch
+
+    from . import _lib
+    from .functional import _f32c, _ptr, _stream
+
+    K = _f32c(K, "K", (None, 3, 3))
+    n = K.shape[0]
+    bbox = bbox_xyxy.to(device=K.device, dtype=torch.int32).contiguous()
+    if bbox.shape != (n, 4):
+        raise ValueError(f"bbox_xyxy: expected shape ({n}, 4), got {tuple(bbox.shape)}")
+    new = lambda c: torch.empty(n, c, dtype=torch.float32, device=K.device)  # noqa: E731
+    out = {"center_angle": new(2), "corner_angle": new(8), "center_pos_enc": new(n_freq * 4), "corner_pos_enc": new(n_freq * 16)}
+    with torch.cuda.device(K.device):
+        rc = _lib.load().hb_kpe_features(_ptr(bbox), _ptr(K), n, int(n_freq), _ptr(out["center_angle"]), _ptr(out["corner_angle"]),
+                                         _ptr(out["center_pos_enc"]), _ptr(out["corner_pos_enc"]), _stream())
+    _lib.check(rc, "hb_kpe_features")
+    return out

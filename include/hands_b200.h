@@ -162,6 +162,12 @@ int hb_mrrpe(const float* j3d_cam_r, const float* j3d_cam_l, const float* gt_j3d
  * joints3d, j3d_full (B,21,3); vertices, v3d_cam (B,778,3); K (B,3,3); cam_t, cam_t_wp (B,3).  Outputs may be NULL. */
 int hb_gt_process(const float* joints3d, const float* vertices, const float* j3d_full, const float* K, int B, float img_res,
                   float* v3d_cam, float* cam_t, float* cam_t_wp, void* stream);
+/* KPE features of the crop boxes (src/datasets/hands_light_dataset.py:259-279, per sample on the CPU in the reference) and
+ * their sinusoidal encodings (src/models/hands_light/model.py:444-460): bbox (n,4) int32 xyxy, K (n,3,3) ->
+ * center_angle (n,2), corner_angle (n,8) [corners (x0,y0),(x0,y1),(x1,y0),(x1,y1)], center_enc (n, n_freq*2*2),
+ * corner_enc (n, n_freq*8*2) laid out [freq][angle][sin,cos].  Outputs may be NULL. */
+int hb_kpe_features(const int32_t* bbox, const float* K, int n, int n_freq, float* center_angle, float* corner_angle,
+                    float* center_enc, float* corner_enc, void* stream);
 
 /* ---- Perspective Crop Layer ------------------------------------------------------------------
  * Replaces: src/datasets/hands_light_dataset.py:354-467 (per-sample CPU closure in the data loader).

@@ -301,6 +301,32 @@ def process_gt_side(buf, pose, betas, j3d_full, K, img_res):
 
 
 # --------------------------------------------------------------------------------------
+# KPE features      (src/datasets/hands_light_dataset.py:259-279, src/models/hands_light/model.py:444-460)
+# --------------------------------------------------------------------------------------
+def kpe_angles(bbox, K):
+    """Per box (numpy float64 arctan2, cast to float32): centre angles (2) and corner angles (8)."""
+    import numpy as np
+
+    bbox, K = np.asarray(bbox, dtype=np.float64), np.asarray(K, dtype=np.float64)
+    center, corner = [], []
+    for b, k in zip(bbox, K):
+        c = (b[:2] + b[2:]) / 2.0
+        center.append(np.array([np.arctan2(c[0] - k[0, 2], k[0, 0]), np.arctan2(c[1] - k[1, 2], k[1, 1])]).astype(np.float32))
+        cr = np.array([[b[0], b[1]], [b[0], b[3]], [b[2], b[1]], [b[2], b[3]]])
+        cr = np.stack([cr[:, 0] - k[0, 2], cr[:, 1] - k[1, 2]], axis=-1)
+        corner.append(np.arctan2(cr, np.array([[k[0, 0], k[1, 1]]])).flatten().astype(np.float32))
+    return torch.from_numpy(np.stack(center)), torch.from_numpy(np.stack(corner))
+
+
+def kpe_pos_enc(angle, L):
+    """model.py:444-460 (compute_center_pos_enc / compute_corner_pos_enc are the same arithmetic)."""
+    bz, c = angle.shape
+    freq_expand = 2 ** torch.arange(L).unsqueeze(0).repeat(bz, 1).reshape(bz, -1, 1)
+    angle_expand = angle.reshape(bz, 1, c)
+    return torch.stack([torch.sin(freq_expand * angle_expand), torch.cos(freq_expand * angle_expand)], dim=-1).reshape(bz, -1).float()
+
+
+# --------------------------------------------------------------------------------------
 # Perspective Crop Layer      (src/datasets/hands_light_dataset.py:354-467)
 # --------------------------------------------------------------------------------------
 def virtual_camera_rotation(p):

@@ -170,6 +170,41 @@ def golden_process_gt():
     np.savez_compressed(os.path.join(HERE, "process_gt.npz"), **save)
 
 
+def golden_kpe():
+    """KPE angles (dataset file lines 259-279, exec'd from the file like the PCL closure) and the sinusoidal encodings
+    (`compute_center_pos_enc` / `compute_corner_pos_enc`, src/models/hands_light/model.py:444-460, exec'd from the file:
+    the module itself needs pytorch3d)."""
+    with open(os.path.join(REF, "src/datasets/hands_light_dataset.py")) as fh:
+        lines = fh.readlines()
+    assert "if 'center' in args.pos_enc" in lines[258] and "targets['corner.r']" in lines[278], (lines[258], lines[278])
+    angle_src = textwrap.dedent("".join(lines[258:279]))
+    with open(os.path.join(REF, "src/models/hands_light/model.py")) as fh:
+        mlines = fh.readlines()
+    assert "def compute_center_pos_enc" in mlines[443] and "return corner_pos_enc" in mlines[459], (mlines[443], mlines[459])
+    enc_ns = {"torch": torch}
+    exec(compile(textwrap.dedent("".join(mlines[443:460])), "<reference pos enc>", "exec"), enc_ns)
+    _, bbox, K = synthetic_pcl_inputs(12, seed=5, img_res=224, smin=40, smax=200)
+    K = K.clone()
+    K[:, 0, 2] += torch.linspace(-8, 8, 12)   # principal point off the image centre
+    K[:, 1, 1] *= 1.03
+    center, corner = [], []
+    for q in range(0, 12, 2):
+        ns = {"np": np, "args": types.SimpleNamespace(pos_enc="center_corner"), "inputs": {}, "targets": {},
+              "r_bbox": bbox[q].numpy(), "l_bbox": bbox[q + 1].numpy(), "intrx_for_enc": K[q].numpy().astype(np.float64)}
+        exec(compile(angle_src, "<reference kpe angles>", "exec"), ns)
+        center += [ns["inputs"]["r_center_angle"]]
+        corner += [ns["inputs"]["r_corner_angle"]]
+        ns["intrx_for_enc"] = K[q + 1].numpy().astype(np.float64)   # the left box with its own intrinsics row
+        exec(compile(angle_src, "<reference kpe angles>", "exec"), ns)
+        center += [ns["inputs"]["l_center_angle"]]
+        corner += [ns["inputs"]["l_corner_angle"]]
+    center, corner = torch.from_numpy(np.stack(center)), torch.from_numpy(np.stack(corner))
+    L = 4
+    me = types.SimpleNamespace(args=types.SimpleNamespace(n_freq_pos_enc=L))
+    np.savez_compressed(os.path.join(HERE, "kpe.npz"), bbox=bbox.numpy(), K=K.numpy(), center=center.numpy(), corner=corner.numpy(), L=L,
+                        center_enc=enc_ns["compute_center_pos_enc"](me, center).numpy(), corner_enc=enc_ns["compute_corner_pos_enc"](me, corner).numpy())
+
+
 def golden_camera_projection():
     B = 32
     rotmat, betas, cam, K = synthetic_head_inputs(B, seed=3, small_s_frac=0.25)
@@ -267,6 +302,7 @@ if __name__ == "__main__":
     golden_rot6d()
     golden_kp_loss()
     golden_process_gt()
+    golden_kpe()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

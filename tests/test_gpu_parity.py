@@ -219,6 +219,20 @@ def test_process_data_light_gt_side(dev, golden_dir):
     assert not out["mano.v3d.cam.r"].requires_grad
 
 
+def test_kpe_features(dev, golden_dir):
+    """KPE angles + encodings, batched on the GPU, against the reference's own lines (golden)."""
+    from hands_b200.pcl import kpe_features
+
+    d = np.load(os.path.join(golden_dir, "kpe.npz"))
+    L = int(d["L"])
+    out = kpe_features(torch.from_numpy(d["bbox"]).to(dev), torch.from_numpy(d["K"]).to(dev), L)
+    assert (out["center_angle"].cpu() - torch.from_numpy(d["center"])).abs().max() <= 1.2e-7
+    assert (out["corner_angle"].cpu() - torch.from_numpy(d["corner"])).abs().max() <= 1.2e-7
+    assert out["center_pos_enc"].shape == (12, L * 4) and out["corner_pos_enc"].shape == (12, L * 16)
+    assert (out["center_pos_enc"].cpu() - torch.from_numpy(d["center_enc"])).abs().max() <= 2e-6
+    assert (out["corner_pos_enc"].cpu() - torch.from_numpy(d["corner_enc"])).abs().max() <= 2e-6
+
+
 @pytest.mark.parametrize("B", [8, 300])
 def test_tensor_core_and_ffma_engines_agree(heads, dev, B):
     """The blendshape contraction runs on tcgen05/TMEM (3xTF32) by default; the register-tiled FFMA engine stays

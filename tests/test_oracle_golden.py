@@ -127,3 +127,13 @@ def test_process_gt_matches_reference(golden_dir):
         for key, name in (("joints3d", "joints3d"), ("vertices", "vertices"), ("v3d.cam", "v3d.cam"), ("cam_t", "cam_t"), ("cam_t.wp", "cam_t.wp")):
             assert torch.equal(o[key], d[f"out_mano.{name}.{side}"]), (side, key)
         assert torch.equal(d[f"out_mano.j3d.cam.{side}"], d[f"in_mano.j3d.full.{side}"])
+
+
+def test_kpe_features_match_reference(golden_dir):
+    """KPE angles and sinusoidal encodings against the reference's own lines (hands_light_dataset.py:259-279, model.py:444-460)."""
+    d = np.load(os.path.join(golden_dir, "kpe.npz"))
+    center, corner = O.kpe_angles(d["bbox"], d["K"])
+    assert np.array_equal(center.numpy(), d["center"]) and np.array_equal(corner.numpy(), d["corner"])
+    L = int(d["L"])
+    assert torch.equal(O.kpe_pos_enc(center, L), torch.from_numpy(d["center_enc"]))
+    assert torch.equal(O.kpe_pos_enc(corner, L), torch.from_numpy(d["corner_enc"]))
