@@ -808,14 +808,16 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
       if (rw * rh > PCL_REG || rw > 64 || rh > 64) {
         if (threadIdx.x == 0) overflow = 1;   // region too large to stage (extreme foreshortening): scan fallback
       } else {
-        // stage the region's gradients with cp.async (all of a thread's loads in flight at once, no register staging);
-        // the sample positions are recomputed (they are not stored in the workspace)
+        // stage the region's gradients with cp.async (all of a thread's loads in flight at once, no register staging); they
+        // are only waited for after the position / binning work below, which does not need them.  (One TMA bulk copy per
+        // region row completing on an mbarrier measured slower, 530 vs 505 us: ~37 copies of ~600 B per tile and crop.)
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
           const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
           const int gidx = (rj0 + rr) * s + (ri0 + cc);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ent_g + idx)), "l"(G + gidx) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        // sample positions are recomputed (they are not stored in the workspace) and binned by the thread that made them
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
           const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
           const float u = tu[cc], v = tv[rr];
@@ -823,12 +825,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
           const float Y = fmaf(P[4], v, P[3] * u) + P[5];
           const float Z = fmaf(P[7], v, P[6] * u) + P[8];
           const float iz = __frcp_rn(1e-8f + Z);
-          ent_p[idx] = make_float2(X * iz - 0.5f, Y * iz - 0.5f);   // same expression as sample_pos_fast
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // ... then bin this thread's own entries (it waited for its own copies; no barrier needed yet)
-        for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
-          const float2 p = ent_p[idx];
+          const float2 p = make_float2(X * iz - 0.5f, Y * iz - 0.5f);   // same expression as sample_pos_fast
+          ent_p[idx] = p;
           const float fx = floorf(p.x) - cx_lo, fy = floorf(p.y) - cy_lo;
           if (fx >= 0.0f && fx < (float)PCL_CELLS && fy >= 0.0f && fy < (float)PCL_CELLS) {
             const int cell = (int)fy * PCL_CELLS + (int)fx;
@@ -836,6 +834,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
             if (slot < PCL_K) lst[cell * PCL_K + slot] = (unsigned short)idx; else overflow = 1;
           }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
     }
     __syncthreads();
