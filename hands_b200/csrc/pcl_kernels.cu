@@ -43,6 +43,17 @@ __device__ __forceinline__ Crop load_crop(const float* __restrict__ rec) {
   return c;
 }
 
+// same from any address space (a record cached in shared memory)
+__device__ __forceinline__ Crop load_crop_any(const float* rec) {
+  Crop c;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c.P[k] = rec[k];
+  c.s = __float_as_int(rec[18]);
+  c.scale = rec[19];
+  c.step = rec[20];
+  return c;
+}
+
 // torch.linspace(0, 1, s)[i]  (CPU kernel: start + step*i below the midpoint, fma(-step, s-1-i, end) above)
 __device__ __forceinline__ float lin01(const Crop& c, int i) {
   if (c.s == 1) return 0.0f;
@@ -720,6 +731,8 @@ constexpr int PCL_REG = 1536;           // region pixels staged in shared memory
 //   3. every source pixel reads the <= 4 cells whose bilinear footprint covers it and accumulates exactly its
 //      contributors, in index order (so the result does not depend on the order the atomics ran in).
 // g_img is written once per pixel: no float atomics, no memset.
+constexpr int PCL_RECS = 4;            // crop records cached in shared memory per image
+
 template <int C, int RT>
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img) {
@@ -742,15 +755,20 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) acc[r][ch] = 0.f;
+  // the records of the image's (first PCL_RECS) crops are fetched once, all fields in flight together, instead of a chain
+  // of dependent global loads per crop
+  __shared__ float recs[PCL_RECS * PF];
+  for (int e = threadIdx.x; e < min(crops_per_img, PCL_RECS) * PF; e += PCL_THREADS) recs[e] = __ldg(params + (size_t)im * crops_per_img * PF + e);
+  __syncthreads();
   for (int k = 0; k < crops_per_img; ++k) {
     const int q = im * crops_per_img + k;
-    const float* rec = params + (size_t)q * PF;
+    const float* rec = k < PCL_RECS ? recs + k * PF : params + (size_t)q * PF;
     // cheap cull: the crop's footprint box (from the setup kernel) against this tile
-    if (__float_as_int(__ldg(rec + 22)) > tx0 + PCL_TS || __float_as_int(__ldg(rec + 23)) < tx0 - 1 ||
-        __float_as_int(__ldg(rec + 24)) > ty0 + PCL_TS || __float_as_int(__ldg(rec + 25)) < ty0 - 1) continue;
-    const int s = __float_as_int(__ldg(rec + 18));
+    if (__float_as_int(*(rec + 22)) > tx0 + PCL_TS || __float_as_int(*(rec + 23)) < tx0 - 1 ||
+        __float_as_int(*(rec + 24)) > ty0 + PCL_TS || __float_as_int(*(rec + 25)) < ty0 - 1) continue;
+    const int s = __float_as_int(*(rec + 18));
     if (s > R) continue;   // outside the supported domain of the backward (see hb_pcl_bwd in the header)
-    const float* base = ws + __float_as_int(__ldg(rec + 21));
+    const float* base = ws + __float_as_int(*(rec + 21));
     const float4* G = reinterpret_cast<const float4*>(base);
     __syncthreads();  // previous crop's readers are done with cnt/lst/ent and the region box
     if (threadIdx.x < 32) {
@@ -759,7 +777,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
       //    of that box under the inverse homography is a convex quad, bounded by the box of its four corners
       float Pi[9];
 #pragma unroll
-      for (int e = 0; e < 9; ++e) Pi[e] = __ldg(rec + 9 + e);
+      for (int e = 0; e < 9; ++e) Pi[e] = *(rec + 9 + e);
       const float sm1 = (float)(s - 1);
       float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
       bool bad = false;
@@ -792,7 +810,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     const int ri0 = box[0], ri1 = box[1], rj0 = box[2], rj1 = box[3];
     if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
     const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
-    const Crop c = load_crop(rec);
+    const Crop c = load_crop_any(rec);
     float P[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) P[e] = c.P[e];
