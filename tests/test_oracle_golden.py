@@ -105,7 +105,7 @@ def test_keypoint_losses_and_metrics_match_reference(golden_dir):
     d = {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(os.path.join(golden_dir, "kp_loss.npz")).items()}
     j3d, j2d = d["j3d"].clone().requires_grad_(True), d["j2d"].clone().requires_grad_(True)
     l3, l2 = O.keypoint_losses(j3d, j2d, d["gt3"], d["gt2"], d["jv"], d["gate3"], d["gate2"])
-    assert abs(float(l3) - float(d["loss3"])) <= 1e-6 * float(d["loss3"]) and abs(float(l2) - float(d["loss2"])) <= 1e-6 * float(d["loss2"])
+    assert abs(float(l3.detach()) - float(d["loss3"])) <= 1e-6 * float(d["loss3"]) and abs(float(l2.detach()) - float(d["loss2"])) <= 1e-6 * float(d["loss2"])
     g3, g2 = torch.autograd.grad(5.0 * l3 + 3.0 * l2, (j3d, j2d))
     assert float((g3 - d["g3"]).abs().max()) <= 1e-6 * float(d["g3"].abs().max()) and float((g2 - d["g2"]).abs().max()) <= 1e-6 * float(d["g2"].abs().max())
     s2, n2, s4, n4 = O.keypoint_metric_sums(d["j3d"], d["j2d"], d["gt3"], d["gt2"], d["jv"], d["hv"], 224.0)
