@@ -7,13 +7,15 @@
 //   pcl_fwd_kernel   : one CTA per (crop, 16 output rows), in sub-blocks that fit a 44 KB shared-memory budget:
 //                      the source footprint is staged by TMA bulk copies, the needed rows of the s x s intermediate
 //                      are gathered from it once, then resized from shared memory; R x R stores are coalesced rows.
-//   pcl_bwd_mid      : transposed resize, vertical pass first (thread = output column, rows straight from global),
-//                      then the windowed horizontal reduction once per intermediate row; writes the intermediate
-//                      gradient and the sample positions into the chunk workspace.
+//   pcl_bwd_mid4     : transposed resize, vertical pass first: a thread owns four adjacent output columns (16-byte
+//                      loads straight from global, the band's rows split over four two-warp groups with carries), then
+//                      the windowed horizontal reduction once per intermediate row, four rows per thread; writes the
+//                      intermediate gradient into the chunk workspace.  (pcl_bwd_mid: scalar-column fallback.)
 //   pcl_bwd_img      : transposed grid_sample, gather form through the inverse homography: the region of the
-//                      intermediate grid that can reach a 32x32 source tile is staged with cp.async and binned into
-//                      per-cell lists; each source pixel collects exactly its contributors in a fixed order, so
-//                      g_img is written once -- no float atomics, no memset, bit-reproducible.
+//                      intermediate grid that can reach a 32x32 source tile is staged with cp.async, its sample
+//                      positions recomputed and binned into per-cell lists; each source pixel collects exactly its
+//                      contributors in a fixed order, so g_img is written once -- no float atomics, no memset,
+//                      bit-reproducible.
 // The fp32 operation order (which products are fused) follows torch's CPU kernels exactly; it was pinned
 // by bit-comparing a numpy emulation against torch 2.11 single-threaded ("PCL exactness").
 #include <climits>

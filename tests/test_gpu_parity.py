@@ -478,6 +478,78 @@ def test_pcl_box_larger_than_image(dev):
         perspective_crop(img.to(dev).requires_grad_(True), bbox.to(dev), K.to(dev), img_res=res)
 
 
+def test_pcl_full_size_properties(dev):
+    """BASELINE config C3 size (1024 source images, two crops each = 2048 crops of 3x224x224), checked through properties
+    that need no CPU oracle: the backward is the exact adjoint of the forward (<F x, y> == <x, F^T y>), the forward is
+    linear in the image, and both are independent of how the batch is sharded (bit-exact)."""
+    from hands_b200.pcl import perspective_crop
+
+    B, cpi, res = 1024, 2, 224
+    n = B * cpi
+    _, bbox, K = synthetic_pcl_inputs(n, seed=3, img_res=res, smin=res // 4, smax=3 * res // 4)
+    bbox, K = bbox.to(dev), K.to(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(B, 3, res, res, generator=g, device=dev).requires_grad_(True)
+    y = torch.randn(n, 3, res, res, generator=g, device=dev)
+    crop, _ = perspective_crop(x, bbox, K, img_res=res, crops_per_img=cpi)
+    (gx,) = torch.autograd.grad(crop, x, grad_outputs=y)
+    lhs = float((crop.detach().double() * y.double()).sum())
+    rhs = float((x.detach().double() * gx.double()).sum())
+    scale = float(crop.detach().double().norm() * y.double().norm())
+    assert abs(lhs - rhs) <= 1e-6 * scale, (lhs, rhs, scale)
+    # linearity of the forward
+    with torch.no_grad():
+        x2 = torch.randn(B, 3, res, res, generator=g, device=dev)
+        c2, _ = perspective_crop(x2, bbox, K, img_res=res, crops_per_img=cpi)
+        c12, _ = perspective_crop(2.5 * x.detach() + x2, bbox, K, img_res=res, crops_per_img=cpi)
+        assert rel(c12, (2.5 * crop.detach() + c2).cpu()) <= 2e-6
+        del c2, c12, x2
+        # shard invariance, forward and backward, bit-exact (a shard boundary inside the 1024-image backward chunk)
+        lo, hi = 300, 812
+        cs, _ = perspective_crop(x.detach()[lo:hi].contiguous(), bbox[lo * cpi:hi * cpi], K[lo * cpi:hi * cpi], img_res=res, crops_per_img=cpi)
+        assert torch.equal(cs, crop.detach()[lo * cpi:hi * cpi])
+    xs = x.detach()[lo:hi].clone().requires_grad_(True)
+    cs, _ = perspective_crop(xs, bbox[lo * cpi:hi * cpi], K[lo * cpi:hi * cpi], img_res=res, crops_per_img=cpi)
+    (gs,) = torch.autograd.grad(cs, xs, grad_outputs=y[lo * cpi:hi * cpi])
+    assert torch.equal(gs, gx[lo:hi])
+
+
+def test_mano_full_size_properties(heads, dev):
+    """BASELINE config C4 per-GPU size (8192 samples -> 8192 hands per side): properties that need no CPU oracle --
+    global-rotation equivariance about the root joint, shard invariance (bit-exact), finger tips == gathered vertices,
+    and linearity of the backward in the upstream gradients."""
+    from hands_b200.synthetic import random_rotmats
+
+    B = 8192
+    rotmat, betas, cam, K = [t.to(dev) for t in synthetic_head_inputs(B, seed=11)]
+    head = heads[False]
+    out = head(rotmat, betas, cam, K)
+    v, j = out["vertices.l"], out["joints3d.l"]
+    assert torch.equal(j[:, 16:], v[:, list(O.TIP_IDS)])
+    Q = random_rotmats(B, torch.Generator().manual_seed(5)).to(dev)
+    outq = head(rotmat, betas, cam, K, pre_rot=Q)
+    root = j[:, :1]
+    assert rel(outq["joints3d.l"][:, 0], j[:, 0].cpu()) <= 1e-5
+    want = torch.einsum("bij,bvj->bvi", Q.double(), (v - root).double()) + root.double()
+    assert rel(outq["vertices.l"], want.cpu()) <= 2e-5
+    sl = slice(5000, 5777)
+    part = head(rotmat[sl].contiguous(), betas[sl].contiguous(), cam[sl].contiguous(), K[sl].contiguous())
+    for key in ("vertices.l", "j3d.cam.l", "j2d.norm.l", "cam_t.l"):
+        assert torch.equal(part[key], out[key][sl]), key
+    # backward: linear in the upstream gradients
+    g = torch.Generator(device=dev).manual_seed(2)
+    w1, w2 = torch.randn(B, 21, 3, generator=g, device=dev), torch.randn(B, 21, 3, generator=g, device=dev)
+
+    def grads(w):
+        r, b = rotmat.clone().requires_grad_(True), betas.clone().requires_grad_(True)
+        o = head(r, b, cam, K)
+        return torch.autograd.grad(o["j3d.cam.l"], (r, b), grad_outputs=w)
+
+    g1, g2, g12 = grads(w1), grads(w2), grads(1.5 * w1 + w2)
+    for a, b, c in zip(g1, g2, g12):
+        assert rel(c, (1.5 * a + b).cpu()) <= 2e-5
+
+
 def test_zero_batch_and_error_paths(dev):
     from hands_b200 import _lib
     from hands_b200.common import rot
