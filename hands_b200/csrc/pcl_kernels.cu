@@ -414,31 +414,6 @@ __device__ __forceinline__ void build_tables(const Crop& c, int R, float* tl1, i
   __syncthreads();
 }
 
-template <int C, bool FROM_GLOBAL>
-__device__ __forceinline__ void transposed_taps(const float* __restrict__ src, size_t chan_stride, const float* tl1, const int* start,
-                                                int m, int s, float (&acc)[C]) {
-  // src points at element d = 0 of the line being reduced (stride 1 along d)
-  const int a0 = start[m], a1 = start[m + 1];
-  for (int d = a0; d < a1; ++d) {
-    const float w = 1.0f - tl1[d];
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, FROM_GLOBAL ? __ldg(src + ch * chan_stride + d) : src[ch * chan_stride + d], acc[ch]);
-  }
-  const int b0 = m > 0 ? start[m - 1] : a0, b1 = m > 0 ? a0 : a0;
-  for (int d = b0; d < b1; ++d) {
-    const float w = tl1[d];
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, FROM_GLOBAL ? __ldg(src + ch * chan_stride + d) : src[ch * chan_stride + d], acc[ch]);
-  }
-  if (m == s - 1) {
-    for (int d = a0; d < a1; ++d) {
-      const float w = tl1[d];
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(w, FROM_GLOBAL ? __ldg(src + ch * chan_stride + d) : src[ch * chan_stride + d], acc[ch]);
-    }
-  }
-}
-
 // Transposed resize (g_out -> intermediate gradient), vertical-first form.
 // One CTA (256 threads) per (crop, band of PCL_JR intermediate rows).
 //   vertical pass  : thread = OUTPUT column x walks down the output rows the band needs, reading g_out straight from
