@@ -89,6 +89,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 # reference CPU path (the oracle), one bounded step
+WORKLOAD = "C4 two-hand (left+right MANO) + 2 PCL crops/sample sharing one source image + projection, fwd+bwd"
+
+
 # ------------------------------------------------------------------------------------------------
 class CpuReferenceStep:
     """Reference torch CPU path for the same step: PCL (grid_sample + interpolate, batched per crop as the
@@ -164,8 +167,9 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": hps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4 two-hand MANO head + 2 PCL crops/sample + projection, fwd+bwd (reference torch CPU path)",
-                   "samples_per_step": samples, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES},
+        "config": {"workload": WORKLOAD, "arm": "reference torch ops on the host CPU (oracle), bounded sample of the same workload",
+                   "samples_per_step": samples, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES, "bbox_side": "U{56..168}",
+                   "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"]},
         "cpu_baseline": {"value": hps, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model(),
                          "sample": f"{samples} samples ({samples * HANDS_PER_SAMPLE} hands + crops) per step; oracle/geometry_oracle.py = reference torch ops on CPU, all host threads"},
         "e2e": {"value": hps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -297,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C4 two-hand (left+right MANO) + 2 PCL crops/sample sharing one source image + projection, fwd+bwd",
+        "config": {"workload": WORKLOAD,
                    "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
