@@ -41,6 +41,16 @@ def test_workspace_sizes_and_argument_errors():
     assert rc == -1 and b"NULL" in lib.hb_last_error_string()
     assert lib.hb_pcl_fwd(None, None, 3, 2, 3, 224, None, None) == -1
     assert lib.hb_matrix_to_axis_angle_fwd(None, 0, None, None) == 0
+    # the rows either side of the path: same conventions (negative code + message, empty batches are no-ops)
+    assert lib.hb_rot6d_to_rotmat_fwd(None, 4, 0, None, None) == -1 and lib.hb_rot6d_to_rotmat_fwd(None, 0, 7, None, None) == -1
+    assert lib.hb_rot6d_to_rotmat_fwd(None, 0, 2, None, None) == 0
+    rc = lib.hb_mano_head_fwd(None, None, 9, None, None, None, None, None, 4, 224.0, 0.1, None, None, None, None, None, None, None, 0, None)
+    assert rc == -1
+    assert lib.hb_kp_loss_fwd(None, None, None, None, None, None, None, None, 5, 224.0, None, None, None) == -1
+    assert lib.hb_kp_loss_bwd(None, None, None, None, None, None, None, 0, None, None, None, None, None) == 0
+    assert lib.hb_mrrpe(None, None, None, None, None, 3, None, None, None) == -1
+    assert lib.hb_gt_process(None, None, None, None, 2, 224.0, None, None, None, None) == -1 and lib.hb_gt_process(None, None, None, None, 0, 224.0, None, None, None, None) == 0
+    assert lib.hb_kpe_features(None, None, 3, 4, None, None, None, None, None) == -1 and lib.hb_kpe_features(None, None, 0, 4, None, None, None, None, None) == 0
 
 
 def test_host_homography_matches_oracle(golden_dir):
@@ -74,6 +84,17 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         rot.matrix_to_axis_angle(torch.eye(3)[None])
     with pytest.raises(RuntimeError, match="no CPU path"):
         transforms.project2d_batch(torch.eye(3)[None], torch.ones(1, 2, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rot.rot6d_to_rotmat(torch.ones(2, 6))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rot.rotation_6d_to_matrix(torch.ones(2, 16, 6))
+    from hands_b200.losses import keypoint_losses
+    from hands_b200.pcl import kpe_features
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        keypoint_losses(torch.zeros(2, 21, 3), torch.zeros(2, 21, 2), torch.zeros(2, 21, 3), torch.zeros(2, 21, 2), torch.ones(2, 21))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        kpe_features(torch.zeros(2, 4, dtype=torch.int32), torch.eye(3).repeat(2, 1, 1), 4)
 
 
 def test_xdict_contract():
