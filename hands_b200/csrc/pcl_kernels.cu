@@ -738,8 +738,12 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   for (int e = threadIdx.x; e < min(crops_per_img, PCL_RECS) * PF; e += PCL_THREADS) recs[e] = __ldg(params + (size_t)im * crops_per_img * PF + e);
   __syncthreads();
   for (int k = 0; k < crops_per_img; ++k) {
-    const int q = im * crops_per_img + k;
-    const float* rec = k < PCL_RECS ? recs + k * PF : params + (size_t)q * PF;
+    if (k >= PCL_RECS) {   // more crops per image than cached records: fetch this one into slot 0 (block-uniform)
+      __syncthreads();
+      if (threadIdx.x < PF) recs[threadIdx.x] = __ldg(params + (size_t)(im * crops_per_img + k) * PF + threadIdx.x);
+      __syncthreads();
+    }
+    const float* rec = recs + (k < PCL_RECS ? k : 0) * PF;   // always shared memory
     // cheap cull: the crop's footprint box (from the setup kernel) against this tile
     if (__float_as_int(*(rec + 22)) > tx0 + PCL_TS || __float_as_int(*(rec + 23)) < tx0 - 1 ||
         __float_as_int(*(rec + 24)) > ty0 + PCL_TS || __float_as_int(*(rec + 25)) < ty0 - 1) continue;
@@ -781,7 +785,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
         overflow = 0;
       }
     } else {
-      for (int idx = threadIdx.x - 32; idx < PCL_CELLS * PCL_CELLS; idx += PCL_THREADS - 32) cnt[idx] = 0;
+      for (int idx = threadIdx.x - 32; idx < (PCL_CELLS * PCL_CELLS + 3) / 4; idx += PCL_THREADS - 32) reinterpret_cast<int4*>(cnt)[idx] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
     const int ri0 = box[0], ri1 = box[1], rj0 = box[2], rj1 = box[3];
@@ -798,7 +802,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     __syncthreads();
     // 2. binning
     {
-      const float inv_rw = 1.0f / (float)rw;
+      // idx / rw for idx < 4096, rw <= 64 by multiply-high: exact while idx * ((2^32 / rw + 1) * rw - 2^32) < 2^32
+      const unsigned magic = rw > 1 ? 0xFFFFFFFFu / (unsigned)rw + 1u : 0u;   // (rw == 1: the quotient is idx itself)
       const float cx_lo = (float)(tx0 - 1), cy_lo = (float)(ty0 - 1);
       if (rw * rh > PCL_REG || rw > 64 || rh > 64) {
         if (threadIdx.x == 0) overflow = 1;   // region too large to stage (extreme foreshortening): scan fallback
@@ -807,14 +812,14 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
         // are only waited for after the position / binning work below, which does not need them.  (One TMA bulk copy per
         // region row completing on an mbarrier measured slower, 530 vs 505 us: ~37 copies of ~600 B per tile and crop.)
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
-          const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
+          const int rr = rw > 1 ? (int)__umulhi((unsigned)idx, magic) : idx, cc = idx - rr * rw;
           const int gidx = (rj0 + rr) * s + (ri0 + cc);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ent_g + idx)), "l"(G + gidx) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         // sample positions are recomputed (they are not stored in the workspace) and binned by the thread that made them
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
-          const int rr = fast_div(idx, rw, inv_rw), cc = idx - rr * rw;
+          const int rr = rw > 1 ? (int)__umulhi((unsigned)idx, magic) : idx, cc = idx - rr * rw;
           const float u = tu[cc], v = tv[rr];
           const float X = fmaf(P[1], v, P[0] * u) + P[2];
           const float Y = fmaf(P[4], v, P[3] * u) + P[5];
@@ -834,21 +839,6 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     }
     __syncthreads();
     const bool slow = overflow != 0;
-    // 2b. put every cell's list in index order (one thread per cell; lists hold 1-2 entries almost always),
-    //     so the accumulation order below does not depend on the order the atomics ran in
-    if (!slow) {
-      for (int cell = threadIdx.x; cell < PCL_CELLS * PCL_CELLS; cell += PCL_THREADS) {
-        const int n = cnt[cell];
-        unsigned short* l = lst + cell * PCL_K;
-        for (int a = 1; a < n; ++a) {
-          const unsigned short v = l[a];
-          int b = a - 1;
-          while (b >= 0 && l[b] > v) { l[b + 1] = l[b]; --b; }
-          l[b + 1] = v;
-        }
-      }
-    }
-    __syncthreads();
     // 3. gather.  A thread owns four vertically adjacent pixels (rows 4*lyb .. 4*lyb+3 of column lx): they touch five
     //    rows of two cells; each cell's entries are read once and feed the pixel below (as its upper taps) and the
     //    pixel above (as its lower taps).  Fixed order: cell row, cell column, list position.
@@ -864,8 +854,21 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
             for (int dx = 0; dx < 2; ++dx) {
               const int cell = (ly0 + cr) * PCL_CELLS + (lx + dx);  // floor(pos) == (sx-1+dx, ty0+ly0+cr-1)
               const int n = cnt[cell];
-              for (int e = 0; e < n; ++e) {
-                const int cur = lst[cell * PCL_K + e];
+              if (n == 0) continue;
+              // the cell's list in index order (the slots were claimed by atomics in arbitrary order): lists hold one
+              // entry almost always, two sometimes, never more than PCL_K = 4 here
+              int ord[PCL_K];
+#pragma unroll
+              for (int e = 0; e < PCL_K; ++e) ord[e] = e < n ? (int)lst[cell * PCL_K + e] : 0x7fffffff;
+              if (n > 1) {
+#define HB_CSWAP(a, b) { const int lo_ = min(ord[a], ord[b]), hi_ = max(ord[a], ord[b]); ord[a] = lo_; ord[b] = hi_; }
+                HB_CSWAP(0, 1) HB_CSWAP(2, 3) HB_CSWAP(0, 2) HB_CSWAP(1, 3) HB_CSWAP(1, 2)
+#undef HB_CSWAP
+              }
+#pragma unroll
+              for (int e = 0; e < PCL_K; ++e) {
+                if (e >= n) break;
+                const int cur = ord[e];
                 const float2 p = ent_p[cur];
                 const float4 g = ent_g[cur];
                 const float wx = 1.0f - fabsf(p.x - fsx);
