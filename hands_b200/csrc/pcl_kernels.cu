@@ -699,6 +699,8 @@ __global__ void __launch_bounds__(PCL_M4T, 3) pcl_bwd_mid4_kernel(const float* _
 constexpr int PCL_TS = 32;              // source tile side
 constexpr int PCL_CELLS = PCL_TS + 1;   // cells = floor(sample position) in [tile-1, tile+31]
 constexpr int PCL_K = 4;                // list capacity per cell (longer lists take the scan fallback)
+constexpr int PCL_CNT_BYTES = (PCL_CELLS * PCL_CELLS * 4 + 15) & ~15;            // counters, padded: the lists stay 8-byte aligned
+constexpr int PCL_LST_BYTES = (PCL_CELLS * PCL_CELLS * 2 * PCL_K + 15) & ~15;
 constexpr int PCL_REG = 1536;           // region pixels staged in shared memory per (tile, crop) (39 x 39; 4 CTAs/SM)
 
 // Transposed grid_sample, gather form.  One CTA per (image, 32x32 source tile); for each crop of the image:
@@ -718,8 +720,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   float4* ent_g = reinterpret_cast<float4*>(img_sm);                                   // [PCL_REG] staged region: gradient ...
   float2* ent_p = reinterpret_cast<float2*>(img_sm + PCL_REG * 16);                    // [PCL_REG] ... and sample position
   int* cnt = reinterpret_cast<int*>(img_sm + PCL_REG * 24);                            // [cells]
-  unsigned short* lst = reinterpret_cast<unsigned short*>(img_sm + PCL_REG * 24 + PCL_CELLS * PCL_CELLS * 4);  // [cells][K] region-local indices
-  float* tu = reinterpret_cast<float*>(img_sm + PCL_REG * 24 + PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K));             // [64] linspace of the region's columns
+  unsigned short* lst = reinterpret_cast<unsigned short*>(img_sm + PCL_REG * 24 + PCL_CNT_BYTES);  // [cells][K] region-local indices
+  float* tu = reinterpret_cast<float*>(img_sm + PCL_REG * 24 + PCL_CNT_BYTES + PCL_LST_BYTES);             // [64] linspace of the region's columns
   float* tv = tu + 64;                                                                                              // [64] ... and rows
   __shared__ int overflow;
   __shared__ int box[4];
@@ -824,8 +826,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
           const float X = fmaf(P[1], v, P[0] * u) + P[2];
           const float Y = fmaf(P[4], v, P[3] * u) + P[5];
           const float Z = fmaf(P[7], v, P[6] * u) + P[8];
-          const float iz = __frcp_rn(1e-8f + Z);
-          const float2 p = make_float2(X * iz - 0.5f, Y * iz - 0.5f);   // same expression as sample_pos_fast
+          const float iz = __fdividef(1.0f, 1e-8f + Z);   // 1-ulp reciprocal: the gradient is continuous in the position
+          const float2 p = make_float2(X * iz - 0.5f, Y * iz - 0.5f);
           ent_p[idx] = p;
           const float fx = floorf(p.x) - cx_lo, fy = floorf(p.y) - cy_lo;
           if (fx >= 0.0f && fx < (float)PCL_CELLS && fy >= 0.0f && fy < (float)PCL_CELLS) {
@@ -857,10 +859,11 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
               if (n == 0) continue;
               // the cell's list in index order (the slots were claimed by atomics in arbitrary order): lists hold one
               // entry almost always, two sometimes, never more than PCL_K = 4 here
-              int ord[PCL_K];
-#pragma unroll
-              for (int e = 0; e < PCL_K; ++e) ord[e] = e < n ? (int)lst[cell * PCL_K + e] : 0x7fffffff;
+              const uint2 pk = *reinterpret_cast<const uint2*>(lst + cell * PCL_K);   // the four 16-bit slots in one load
+              int ord[PCL_K] = {(int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)(pk.y & 0xffffu), (int)(pk.y >> 16)};
               if (n > 1) {
+#pragma unroll
+                for (int e = 1; e < PCL_K; ++e) ord[e] = e < n ? ord[e] : 0x7fffffff;
 #define HB_CSWAP(a, b) { const int lo_ = min(ord[a], ord[b]), hi_ = max(ord[a], ord[b]); ord[a] = lo_; ord[b] = hi_; }
                 HB_CSWAP(0, 1) HB_CSWAP(2, 3) HB_CSWAP(0, 2) HB_CSWAP(1, 3) HB_CSWAP(1, 2)
 #undef HB_CSWAP
@@ -1004,7 +1007,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   auto mid4_kernel = (R == 224) ? pcl_bwd_mid4_kernel<C, 224> : pcl_bwd_mid4_kernel<C, 0>;
   if (mid4) HB_CUDA(cudaFuncSetAttribute(mid4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid4));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
-  const size_t smem_img = (size_t)PCL_REG * 24 + (size_t)PCL_CELLS * PCL_CELLS * (4 + 2 * PCL_K) + 128 * sizeof(float);
+  const size_t smem_img = (size_t)PCL_REG * 24 + PCL_CNT_BYTES + PCL_LST_BYTES + 128 * sizeof(float);
   auto img_kernel = (R == 224) ? pcl_bwd_img_kernel<C, 224> : pcl_bwd_img_kernel<C, 0>;
   HB_CUDA(cudaFuncSetAttribute(img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
   for (int ch = 0; ch < n_chunks; ++ch) {
