@@ -394,7 +394,7 @@ def test_pcl_forward_against_golden(dev, golden_dir):
         assert torch.equal(r2[0].cpu(), torch.from_numpy(g["full_rot"][j]))
 
 
-@pytest.mark.parametrize("B,cpi,res,smooth", [(6, 1, 224, False), (4, 2, 224, True), (3, 2, 96, False)])
+@pytest.mark.parametrize("B,cpi,res,smooth", [(6, 1, 224, False), (4, 2, 224, True), (3, 2, 96, False), (2, 5, 100, False), (1, 7, 224, True)])
 def test_pcl_forward_backward_against_oracle(dev, B, cpi, res, smooth):
     from hands_b200.pcl import perspective_crop
 
