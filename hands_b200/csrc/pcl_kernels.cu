@@ -852,14 +852,18 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
         if (sx < R) {
 #pragma unroll
           for (int cr = 0; cr < 5; ++cr) {
+            // counts and lists of the row's two cells are fetched together, before any of them is used (independent
+            // shared-memory loads in flight instead of a dependent chain per cell)
+            const int cell0 = (ly0 + cr) * PCL_CELLS + lx;   // floor(pos) == (sx-1+dx, ty0+ly0+cr-1)
+            const int n2[2] = {cnt[cell0], cnt[cell0 + 1]};
+            const uint2 pk2[2] = {*reinterpret_cast<const uint2*>(lst + cell0 * PCL_K), *reinterpret_cast<const uint2*>(lst + (cell0 + 1) * PCL_K)};
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-              const int cell = (ly0 + cr) * PCL_CELLS + (lx + dx);  // floor(pos) == (sx-1+dx, ty0+ly0+cr-1)
-              const int n = cnt[cell];
+              const int n = n2[dx];
               if (n == 0) continue;
               // the cell's list in index order (the slots were claimed by atomics in arbitrary order): lists hold one
               // entry almost always, two sometimes, never more than PCL_K = 4 here
-              const uint2 pk = *reinterpret_cast<const uint2*>(lst + cell * PCL_K);   // the four 16-bit slots in one load
+              const uint2 pk = pk2[dx];   // the four 16-bit slots in one load
               int ord[PCL_K] = {(int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)(pk.y & 0xffffu), (int)(pk.y >> 16)};
               if (n > 1) {
 #pragma unroll
