@@ -857,27 +857,15 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
             const int cell0 = (ly0 + cr) * PCL_CELLS + lx;   // floor(pos) == (sx-1+dx, ty0+ly0+cr-1)
             const int n2[2] = {cnt[cell0], cnt[cell0 + 1]};
             const uint2 pk2[2] = {*reinterpret_cast<const uint2*>(lst + cell0 * PCL_K), *reinterpret_cast<const uint2*>(lst + (cell0 + 1) * PCL_K)};
+            // ... and so are the first entries of both lists (index clamped: an empty cell's slot holds stale bits)
+            const int c0 = min((int)(pk2[0].x & 0xffffu), PCL_REG - 1), c1 = min((int)(pk2[1].x & 0xffffu), PCL_REG - 1);
+            const float2 p2[2] = {ent_p[c0], ent_p[c1]};
+            const float4 g2[2] = {ent_g[c0], ent_g[c1]};
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
               const int n = n2[dx];
               if (n == 0) continue;
-              // the cell's list in index order (the slots were claimed by atomics in arbitrary order): lists hold one
-              // entry almost always, two sometimes, never more than PCL_K = 4 here
-              const uint2 pk = pk2[dx];   // the four 16-bit slots in one load
-              int ord[PCL_K] = {(int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)(pk.y & 0xffffu), (int)(pk.y >> 16)};
-              if (n > 1) {
-#pragma unroll
-                for (int e = 1; e < PCL_K; ++e) ord[e] = e < n ? ord[e] : 0x7fffffff;
-#define HB_CSWAP(a, b) { const int lo_ = min(ord[a], ord[b]), hi_ = max(ord[a], ord[b]); ord[a] = lo_; ord[b] = hi_; }
-                HB_CSWAP(0, 1) HB_CSWAP(2, 3) HB_CSWAP(0, 2) HB_CSWAP(1, 3) HB_CSWAP(1, 2)
-#undef HB_CSWAP
-              }
-#pragma unroll
-              for (int e = 0; e < PCL_K; ++e) {
-                if (e >= n) break;
-                const int cur = ord[e];
-                const float2 p = ent_p[cur];
-                const float4 g = ent_g[cur];
+              auto add = [&](const float2 p, const float4 g) {
                 const float wx = 1.0f - fabsf(p.x - fsx);
                 const float gv[4] = {g.x, g.y, g.z, g.w};
                 if (cr < 4) {   // pixel row cr: floor(pos.y) == sy - 1
@@ -890,6 +878,21 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
 #pragma unroll
                   for (int ch = 0; ch < C; ++ch) acc[cr - 1][ch] = fmaf(w, gv[ch], acc[cr - 1][ch]);
                 }
+              };
+              if (n == 1) { add(p2[dx], g2[dx]); continue; }   // the usual case
+              // several entries: in index order (the slots were claimed by atomics in arbitrary order); never more than
+              // PCL_K = 4 here
+              const uint2 pk = pk2[dx];
+              int ord[PCL_K] = {(int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)(pk.y & 0xffffu), (int)(pk.y >> 16)};
+#pragma unroll
+              for (int e = 1; e < PCL_K; ++e) ord[e] = e < n ? ord[e] : 0x7fffffff;
+#define HB_CSWAP(a, b) { const int lo_ = min(ord[a], ord[b]), hi_ = max(ord[a], ord[b]); ord[a] = lo_; ord[b] = hi_; }
+              HB_CSWAP(0, 1) HB_CSWAP(2, 3) HB_CSWAP(0, 2) HB_CSWAP(1, 3) HB_CSWAP(1, 2)
+#undef HB_CSWAP
+#pragma unroll
+              for (int e = 0; e < PCL_K; ++e) {
+                if (e >= n) break;
+                add(ent_p[ord[e]], ent_g[ord[e]]);
               }
             }
           }
