@@ -820,6 +820,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         // sample positions are recomputed (they are not stored in the workspace) and binned by the thread that made them
+#pragma unroll 2
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
           const int rr = rw > 1 ? (int)__umulhi((unsigned)idx, magic) : idx, cc = idx - rr * rw;
           const float u = tu[cc], v = tv[rr];
