@@ -664,9 +664,9 @@ __global__ void __launch_bounds__(PCL_M4T, 3) pcl_bwd_mid4_kernel(const float* _
   __syncthreads();
   // horizontal pass
   const int nq = (nrows + 3) >> 2;
-  const float inv_s = 1.0f / (float)s;
+  const unsigned magic_s = s > 1 ? 0xFFFFFFFFu / (unsigned)s + 1u : 0u;   // idx / s by multiply-high (idx < 4 s: exact)
   for (int idx = tid; idx < nq * s; idx += PCL_M4T) {
-    const int rq = fast_div(idx, s, inv_s), i = idx - rq * s;
+    const int rq = s > 1 ? (int)__umulhi((unsigned)idx, magic_s) : idx, i = idx - rq * s;
     const int wa = start[i], we = start[i + 1], wb = i > 0 ? start[i - 1] : wa;
     const float* v0 = Vb + (size_t)(rq * 4) * C * R;
     float h[4][C];
@@ -813,6 +813,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
         // stage the region's gradients with cp.async (all of a thread's loads in flight at once, no register staging); they
         // are only waited for after the position / binning work below, which does not need them.  (One TMA bulk copy per
         // region row completing on an mbarrier measured slower, 530 vs 505 us: ~37 copies of ~600 B per tile and crop.)
+#pragma unroll 2
         for (int idx = threadIdx.x; idx < rw * rh; idx += PCL_THREADS) {
           const int rr = rw > 1 ? (int)__umulhi((unsigned)idx, magic) : idx, cc = idx - rr * rw;
           const int gidx = (rj0 + rr) * s + (ri0 + cc);
