@@ -292,17 +292,18 @@ class PerspectiveCropFunction(torch.autograd.Function):
         dev = img.device
         if bbox.dtype not in (torch.int16, torch.int32, torch.int64):
             raise TypeError(f"bbox: expected an integer tensor, got {bbox.dtype}")
-        bbox = bbox.to(device=dev, dtype=torch.int32).contiguous()
         if tuple(bbox.shape) != (n, 4):
             raise ValueError(f"bbox: expected ({n},4), got {tuple(bbox.shape)}")
-        K = _f32c(K.to(dev) if isinstance(K, torch.Tensor) else K, "K", (n, 3, 3))
         if img.requires_grad and n > 0:
             # The backward packs an s x s intermediate per crop into a workspace sized for s <= R, which the reference
-            # guarantees by clipping boxes to the image (common/data_utils.py:508).  Fail loudly otherwise.
+            # guarantees by clipping boxes to the image (common/data_utils.py:508).  Fail loudly otherwise.  Checked on the
+            # tensor as given: free for boxes that arrive on the host (the data loader's), one sync for device boxes.
             side = int((bbox[:, 2:] - bbox[:, :2]).max())
             if side > R:
                 raise ValueError(f"perspective_crop backward needs boxes no larger than the image (side {side} > {R}); "
                                  "clip the boxes or call under torch.no_grad()")
+        bbox = bbox.to(device=dev, dtype=torch.int32).contiguous()
+        K = _f32c(K.to(dev) if isinstance(K, torch.Tensor) else K, "K", (n, 3, 3))
         params = torch.empty(n, _lib.PCL_PARAM_FLOATS, dtype=torch.float32, device=dev)
         rot = torch.empty(n, 3, 3, dtype=torch.float32, device=dev)
         out = torch.empty(n, C, R, R, dtype=torch.float32, device=dev)
