@@ -28,12 +28,36 @@ def _nvcc():
     return exe
 
 
+STAMP = os.path.join(HERE, "lib", "build.sha256")
+HEADER = os.path.join(HERE, "..", "include", "hands_b200.h")
+
+
+def source_digest():
+    """sha256 over every file the library is built from plus the flags.  Stored beside the .so at build time; a
+    mismatch means the binary is stale (mtimes do not survive the copy to a GPU box, content does)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for path in sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [HEADER]:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    h.update(repr((NVCC_FLAGS, sorted(PER_FILE_FLAGS.items()))).encode())
+    return h.hexdigest()
+
+
+def header_version():
+    import re
+
+    with open(HEADER) as fh:
+        return int(re.search(r"#define\s+HB_VERSION\s+(\d+)", fh.read()).group(1))
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "hands_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
@@ -58,6 +82,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed")
     with open(os.path.join(HERE, "lib", "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
+    with open(STAMP, "w") as fh:
+        fh.write(source_digest())
     if verbose:
         print("\n".join(log))
     return LIB

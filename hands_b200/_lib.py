@@ -70,14 +70,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
-        path = _build.build()
+    path = _build.build()   # no-op when the binary's source digest matches the tree; rebuilds a stale or missing one
     lib = ctypes.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError here means the .so does not match include/hands_b200.h
         fn.restype = res
         fn.argtypes = args
+    if lib.hb_version() != _build.header_version():
+        raise RuntimeError(f"libhands_b200.so reports version {lib.hb_version()}, include/hands_b200.h declares {_build.header_version()}")
     _lib = lib
     return lib
 

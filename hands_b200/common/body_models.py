@@ -72,6 +72,18 @@ def load_mano_pkl(path, flat_hand_mean=False):
     }
 
 
+class VertexJointSelector(nn.Module):
+    """smplx's vertex_joint_selector: holds the finger-tip vertex ids (vertex_ids['mano']) as the buffer
+    `extra_joints_idxs`; the gather itself happens inside the skinning kernel (bit-exact copy)."""
+
+    def __init__(self, tip_ids):
+        super().__init__()
+        self.register_buffer("extra_joints_idxs", torch.as_tensor(tip_ids).long().clone())
+
+    def forward(self, vertices, joints):
+        return torch.cat([joints, vertices.index_select(1, self.extra_joints_idxs)], dim=1)
+
+
 class MANOLayer(nn.Module):
     """B200-native stand-in for `smplx.MANO(model_path, use_pca=False, is_rhand=..., flat_hand_mean=...)`."""
 
@@ -80,11 +92,16 @@ class MANOLayer(nn.Module):
     def __init__(self, buffers, is_rhand=True, create_transl=False):
         super().__init__()
         self.is_rhand = is_rhand
+        # state_dict key set of smplx.MANO(use_pca=False) [smplx-recalled, SURVEY.md App. A]: buffers faces_tensor, v_template,
+        # shapedirs, J_regressor, posedirs, parents, lbs_weights, hand_mean, pose_mean, vertex_joint_selector.extra_joints_idxs;
+        # parameters betas, global_orient, hand_pose (+ transl).  The reference loads checkpoints strictly
+        # (common/abstract_pl.py:42-44), so nothing else may be persistent here.
         for name in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "pose_mean"):
             self.register_buffer(name, buffers[name].float().clone())
+        self.register_buffer("hand_mean", buffers["pose_mean"][3:].float().clone())
         self.register_buffer("parents", buffers["parents"].long().clone())
         self.register_buffer("faces_tensor", buffers["faces"].long().clone())
-        self.register_buffer("tip_ids", buffers["tip_ids"].long().clone())
+        self.vertex_joint_selector = VertexJointSelector(buffers["tip_ids"])
         self.faces = buffers["faces"].cpu().numpy()
         # smplx keeps 1-row default parameters in parameters()/state_dict()
         self.betas = nn.Parameter(torch.zeros(1, 10))
@@ -94,17 +111,48 @@ class MANOLayer(nn.Module):
             self.transl = nn.Parameter(torch.zeros(1, 3))
         self._handles = {}
 
+    @property
+    def tip_ids(self):
+        return self.vertex_joint_selector.extra_joints_idxs
+
+    _CONST_NAMES = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "parents", "pose_mean")
+
+    def _const_buffers(self):
+        bufs = {k: getattr(self, k) for k in self._CONST_NAMES}
+        bufs["tip_ids"] = self.tip_ids
+        return bufs
+
     def handle(self, device):
-        """hb_mano* for `device` (built on first use; rebuilt if the module moved)."""
-        key = (device.type, device.index)
-        h = self._handles.get(key)
-        if h is None:
-            if device.type != "cuda":
-                raise RuntimeError("hands_b200 MANO layer has no CPU path; move the module and inputs to a CUDA device")
-            bufs = {k: getattr(self, k) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "parents", "pose_mean", "tip_ids")}
-            h = ManoHandle(bufs, device)
-            self._handles[key] = h
-        return h
+        """hb_mano* for `device`.  The device-side constant blob is rebuilt whenever a buffer it was made from has been
+        replaced or edited in place (load_state_dict, .to(), manual edits): the cache key holds every buffer's
+        (data_ptr, _version)."""
+        if device.type != "cuda":
+            raise RuntimeError("hands_b200 MANO layer has no CPU path; move the module and inputs to a CUDA device")
+        bufs = self._const_buffers()
+        stamp = tuple((t.data_ptr(), t._version) for t in bufs.values())
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        hit = self._handles.get(key)
+        if hit is None or hit[0] != stamp:
+            hit = (stamp, ManoHandle(bufs, device))
+            self._handles[key] = hit
+        return hit[1]
+
+    # the handle cache holds ctypes pointers to device memory: never copied or pickled with the module
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"] = {}
+        return state
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """Strict loading of reference checkpoints (common/abstract_pl.py:42-44): smplx versions differ in which helper
+        tensors they register (`body_pose`, `hand_components`, `hand_mean`), so keys under this module's prefix that do not
+        exist on one side are neither 'missing' nor 'unexpected'."""
+        m0, u0 = len(missing_keys), len(unexpected_keys)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        tolerated = {prefix + k for k in ("body_pose", "hand_components", "hand_mean", "transl")}
+        missing_keys[m0:] = [k for k in missing_keys[m0:] if k not in tolerated]
+        unexpected_keys[u0:] = [k for k in unexpected_keys[u0:] if k not in tolerated]
+        self._handles = {}
 
     def forward(self, betas=None, global_orient=None, hand_pose=None, transl=None, return_verts=True, return_full_pose=False, **kwargs):
         ref = next(t for t in (betas, global_orient, hand_pose, self.v_template) if t is not None)

@@ -32,7 +32,7 @@ int check_launch(const char* what) {
 using namespace hb;
 
 extern "C" const char* hb_last_error_string(void) { return g_err; }
-extern "C" int hb_version(void) { return 110; }
+extern "C" int hb_version(void) { return HB_VERSION; }
 extern "C" int hb_mano_set_tensor_core(int on) { const int prev = g_mano_tc; g_mano_tc = on ? 1 : 0; return prev; }
 extern "C" uint64_t hb_launch_count(void) { return g_launches.load(); }
 

@@ -31,7 +31,8 @@ __host__ __device__ inline int pcl_homography64(const int32_t* bb, const float* 
   const double cx = (double)(bb[0] + bb[2]) / 2.0, cy = (double)(bb[1] + bb[3]) / 2.0;
   const int w = bb[2] - bb[0], h = bb[3] - bb[1];
   int s = w > h ? w : h;
-  if (s == 0) s = img_res;
+  if (s <= 0) s = img_res;   // empty box -> whole image (hands_light_dataset.py:450-454); an inverted box (the reference raises in
+                             // linspace; the Python wrapper rejects it) is treated the same so the kernels stay in bounds
   const double p0 = Ki[0] * cx + Ki[1] * cy + Ki[2], p1 = Ki[3] * cx + Ki[4] * cy + Ki[5], p2 = Ki[6] * cx + Ki[7] * cy + Ki[8];
   const double x = p0, y = p1;
   const double n1x = sqrt(1.0 + x * x), d1x = 1.0 / n1x;

@@ -284,6 +284,7 @@ class PerspectiveCropFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, bbox, K, crops_per_img):
         lib = _lib.load()
+        needs_grad = bool(img.requires_grad)   # read before _f32c: .contiguous() of a strided image is a new tensor
         img = _f32c(img, "img")
         if img.dim() != 4 or img.shape[2] != img.shape[3]:
             raise ValueError(f"img: expected (B,C,R,R), got {tuple(img.shape)}")
@@ -294,12 +295,17 @@ class PerspectiveCropFunction(torch.autograd.Function):
             raise TypeError(f"bbox: expected an integer tensor, got {bbox.dtype}")
         if tuple(bbox.shape) != (n, 4):
             raise ValueError(f"bbox: expected ({n},4), got {tuple(bbox.shape)}")
-        if img.requires_grad and n > 0:
+        if n > 0 and (needs_grad or not bbox.is_cuda):
+            # Checked on the tensor as given: free for boxes that arrive on the host (the data loader's), one sync for
+            # device boxes (only paid when a gradient is requested).
+            wh = bbox[:, 2:] - bbox[:, :2]
+            side, low = int(wh.max()), int(wh.min())
+            if low < 0:
+                # the reference raises in torch.linspace(0, 1, s) for s < 0 (hands_light_dataset.py:390-391)
+                raise ValueError(f"perspective_crop: inverted box (x1 < x0 or y1 < y0, extent {low})")
             # The backward packs an s x s intermediate per crop into a workspace sized for s <= R, which the reference
-            # guarantees by clipping boxes to the image (common/data_utils.py:508).  Fail loudly otherwise.  Checked on the
-            # tensor as given: free for boxes that arrive on the host (the data loader's), one sync for device boxes.
-            side = int((bbox[:, 2:] - bbox[:, :2]).max())
-            if side > R:
+            # guarantees by clipping boxes to the image (common/data_utils.py:508).  Fail loudly otherwise.
+            if needs_grad and side > R:
                 raise ValueError(f"perspective_crop backward needs boxes no larger than the image (side {side} > {R}); "
                                  "clip the boxes or call under torch.no_grad()")
         bbox = bbox.to(device=dev, dtype=torch.int32).contiguous()

@@ -26,8 +26,15 @@ class MANOHead(nn.Module):
         pre_rot (extension, default None): (B,3,3) R_virt2orig fused onto the global orientation
                 (the PCL fix-up of hands_light/model.py:330-334) instead of a separate in-place bmm.
         """
-        rotmat_original = rotmat.clone()
         pose = rotmat if rotmat.shape[-1] == 48 else rotmat.reshape(-1, 16, 3, 3)
+        if pre_rot is not None:
+            # the reference rotates hmr_output["pose"][:,0] in place BEFORE this head (hands_light/model.py:330-334), so the
+            # `pose` it returns (mano_head.py:30,61), which feeds the pose loss (loss_arctic_sf.py:23-27), is the ROTATED one
+            from ....pcl import apply_virtual_rotation
+
+            rotmat_original = apply_virtual_rotation(pre_rot, pose)
+        else:
+            rotmat_original = rotmat.clone()
         handle = self.mano.handle(shape.device)
         vertices, v3d_cam, joints3d, j3d_cam, j2d_norm, cam_t = ManoHeadFunction.apply(
             handle, pose, shape, cam, K, None, pre_rot, float(self.img_res), 0.1
@@ -66,5 +73,10 @@ class MANOHead(nn.Module):
         output["v3d.cam"] = v3d_cam
         output["j2d.norm"] = j2d_norm
         output["beta"] = shape
-        output["pose"] = Rot6dToRotmatFunction.apply(x6.reshape(-1, 6), layout).reshape(B, 16, 3, 3)
+        pose_mats = Rot6dToRotmatFunction.apply(x6.reshape(-1, 6), layout).reshape(B, 16, 3, 3)
+        if pre_rot is not None:   # as in forward(): the returned pose carries the rotated global orientation
+            from ....pcl import apply_virtual_rotation
+
+            pose_mats = apply_virtual_rotation(pre_rot, pose_mats)
+        output["pose"] = pose_mats
         return output.postfix(".r" if self.is_rhand else ".l")

@@ -123,6 +123,10 @@ class GeometryStep:
     def run(self, overlap=True):
         """Enqueue one full fwd+bwd step.  Work is ordered after everything already on the current
         stream and the current stream waits for it, so callers can bracket it with events."""
+        with torch.cuda.device(self.dev):   # launches and cudaFuncSetAttribute target self.dev whatever the caller's device
+            self._run(overlap)
+
+    def _run(self, overlap):
         cur = torch.cuda.current_stream(self.dev)
         if not overlap or not (self.with_pcl and self.with_mano):
             if self.with_pcl:

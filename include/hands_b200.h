@@ -53,6 +53,7 @@ typedef struct hb_mano hb_mano; /* opaque: MANO constants of one hand side on on
 #define HB_ROT6D_COLS 1        /* src/models/hamer_light/geometry.py:47-62, src/models/handoccnet_light/mano_head.py:132-141: a1=x[0:3], a2=x[3:6], COLUMNS */
 #define HB_ROT6D_COLS_PAIRED 2 /* common/rot.py:367-381: a1=x[0,2,4], a2=x[1,3,5], COLUMNS */
 
+#define HB_VERSION 200 /* hb_version() of a matching binary */
 const char* hb_last_error_string(void);
 int hb_version(void);
 

@@ -17,3 +17,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_terminal_summary(terminalreporter):
+    import _tol
+
+    out = _tol.dump(ROOT)
+    if out:
+        terminalreporter.write_line(f"tolerance branches: {out['tally']} of {out['n']} checks (gpurun_out/tolerance_branches.json)")
+        for r in out["widened"]:
+            terminalreporter.write_line(f"  {r['branch']}: {r['name']} err {r['err']:.3e} tol {r['tol']:.0e} own {r['own']}")

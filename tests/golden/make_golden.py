@@ -294,6 +294,97 @@ def golden_pcl():
     np.savez_compressed(os.path.join(HERE, "pcl.npz"), **out)
 
 
+def golden_mesh_constants():
+    """Wrist-seal constants and `seal_mano_mesh` of the reference (common/body_models.py:35-72).  The module itself does
+    not import (trimesh/smplx/$MANO_DIR at import), so the three top-level statements are exec'd from the file's own AST --
+    nothing is copied into this repository."""
+    import ast
+
+    with open(os.path.join(REF, "common", "body_models.py")) as fh:
+        tree = ast.parse(fh.read())
+    want = {"SEAL_FACES_R", "CIRCLE_V_ID", "seal_mano_mesh"}
+    body = [n for n in tree.body
+            if (isinstance(n, ast.Assign) and any(getattr(t, "id", None) in want for t in n.targets))
+            or (isinstance(n, ast.FunctionDef) and n.name in want)]
+    assert len(body) == 3
+    ns = {"np": np, "torch": torch}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "ref_body_models_constants", "exec"), ns)
+    g = torch.Generator().manual_seed(21)
+    v3d = torch.randn(3, 778, 3, generator=g)
+    faces = torch.randint(0, 778, (1538, 3), generator=g)
+    out = {"SEAL_FACES_R": np.array(ns["SEAL_FACES_R"], dtype=np.int64), "CIRCLE_V_ID": np.asarray(ns["CIRCLE_V_ID"], dtype=np.int64),
+           "v3d": v3d.numpy(), "faces": faces.numpy()}
+    for name, is_rhand in (("r", True), ("l", False)):
+        sv, sf = ns["seal_mano_mesh"](v3d, faces, is_rhand)
+        out[f"sealed_v_{name}"] = sv.numpy()
+        out[f"sealed_f_{name}"] = sf.numpy()
+    np.savez_compressed(os.path.join(HERE, "mesh_constants.npz"), **out)
+
+
+def golden_mano_head_reference_source():
+    """The reference's OWN `MANOHead` (src/nets/hand_heads/mano_head.py:12-65), imported from where it lies and run on CPU.
+    Its only un-importable dependency, `common.body_models` (needs smplx + the licensed pickles), is replaced by a stub
+    module whose `build_mano_aa` returns the oracle's MANO restatement over the seeded synthetic buffers; every other
+    module it imports (common.rot / camera / transforms / data_utils / xdict) is the reference's.  This pins the head chain
+    a10-a14 (log map -> MANO call -> camera -> projection -> normalisation -> nine xdict keys) GIVEN the MANO layer; the
+    MANO arithmetic inside the stub stays 'parity unpinned'."""
+    import importlib.util
+    from collections import namedtuple
+
+    from hands_b200.synthetic import synthetic_mano_buffers
+    from oracle import geometry_oracle as O
+
+    Out = namedtuple("Out", ["vertices", "joints"])
+
+    class OracleMano(torch.nn.Module):
+        def __init__(self, is_rhand):
+            super().__init__()
+            self.buf = synthetic_mano_buffers(is_rhand)
+
+        def forward(self, betas=None, global_orient=None, hand_pose=None, transl=None):
+            return Out(*O.mano_forward(self.buf, betas, global_orient, hand_pose, transl))
+
+    stub = types.ModuleType("common.body_models")
+    stub.build_mano_aa = lambda is_rhand, create_transl=False, flat_hand=False: OracleMano(is_rhand)
+    saved = sys.modules.get("common.body_models")
+    sys.modules["common.body_models"] = stub
+    try:
+        spec = importlib.util.spec_from_file_location("ref_mano_head", os.path.join(REF, "src", "nets", "hand_heads", "mano_head.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            del sys.modules["common.body_models"]
+        else:
+            sys.modules["common.body_models"] = saved
+    out = {}
+    B = 12
+    for name, is_rhand in (("r", True), ("l", False)):
+        head = mod.MANOHead(is_rhand, 1000.0, 224.0)
+        rotmat, betas, cam, K = synthetic_head_inputs(B, seed=41 + int(is_rhand), small_s_frac=0.25)
+        g = torch.Generator().manual_seed(5 + int(is_rhand))
+        w = {"v3d.cam": torch.randn(B, 778, 3, generator=g), "j3d.cam": torch.randn(B, 21, 3, generator=g), "j2d.norm": torch.randn(B, 21, 2, generator=g)}
+        r, b, c = rotmat.clone().requires_grad_(True), betas.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+        o = head(r, b, c, K)
+        pf = "." + name
+        assert sorted(o.keys()) == sorted(k + pf for k in ["cam_t.wp", "cam_t", "joints3d", "vertices", "j3d.cam", "v3d.cam", "j2d.norm", "beta", "pose"])
+        loss = sum((o[k + pf] * w[k]).sum() for k in w)
+        gr, gb, gc = torch.autograd.grad(loss, (r, b, c))
+        out[f"seed_{name}"] = np.array(41 + int(is_rhand))
+        for k in ["cam_t", "joints3d", "vertices", "j3d.cam", "v3d.cam", "j2d.norm", "pose", "beta", "cam_t.wp"]:
+            out[f"{k}_{name}"] = o[k + pf].detach().numpy()
+        for k, v in w.items():
+            out[f"w_{k}_{name}"] = v.numpy()
+        out[f"g_rotmat_{name}"], out[f"g_betas_{name}"], out[f"g_cam_{name}"] = gr.numpy(), gb.numpy(), gc.numpy()
+        # axis-angle input branch (rotmat.shape[-1] == 48, mano_head.py:31)
+        aa = ref_rot.matrix_to_axis_angle(rotmat.reshape(-1, 3, 3)).reshape(-1, 48)
+        o2 = head(aa, betas, cam, K)
+        out[f"aa_{name}"] = aa.numpy()
+        out[f"aa_j2d.norm_{name}"] = o2["j2d.norm" + pf].detach().numpy()
+        out[f"aa_v3d.cam_{name}"] = o2["v3d.cam" + pf].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "mano_head_ref.npz"), **{k: (v.astype(np.float32) if v.dtype == np.float64 else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     golden_logmap()
@@ -303,6 +394,8 @@ if __name__ == "__main__":
     golden_kp_loss()
     golden_process_gt()
     golden_kpe()
+    golden_mesh_constants()
+    golden_mano_head_reference_source()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -13,6 +13,7 @@ import torch
 
 from hands_b200.synthetic import synthetic_head_inputs, synthetic_mano_buffers, synthetic_pcl_inputs
 from oracle import geometry_oracle as O
+from _tol import tol_check
 
 pytestmark = pytest.mark.gpu
 
@@ -56,10 +57,10 @@ def test_head_forward(heads, dev, B, is_rhand, edge):
     for key in ["vertices", "joints3d", "v3d.cam", "j3d.cam", "cam_t"]:
         own = rel(ref32[key], ref64[key])
         r = rel(out[key + pf], ref64[key])
-        assert r <= max(1e-5, 3 * own), (key, r, own)
+        tol_check(f"head_fwd[{B},{edge}].{key}", r, 1e-5, own)
     px = (out["j2d.norm" + pf].double().cpu() - ref64["j2d.norm"]).abs().max() * IMG_RES / 2
     own_px = (ref32["j2d.norm"].double() - ref64["j2d.norm"]).abs().max() * IMG_RES / 2
-    assert px <= max(1e-3, 3 * float(own_px)), (float(px), float(own_px))
+    tol_check(f"head_fwd[{B},{edge}].j2d_px", px, 1e-3, own_px)
     assert torch.equal(out["pose" + pf].cpu(), rotmat) and torch.equal(out["beta" + pf].cpu(), betas)
     assert out["vertices" + pf].shape == (B, 778, 3) and out["joints3d" + pf].shape == (B, 21, 3) and out["j2d.norm" + pf].shape == (B, 21, 2)
     # fingertip gather is indexing: bit-exact against our own vertices
@@ -98,7 +99,7 @@ def test_head_backward(heads, dev, B, is_rhand, edge, keys):
     for name, a, r64, r32 in zip(("rotmat", "betas", "cam"), got, ref64, ref32):
         own = rel(r32, r64)
         r = rel(a, r64)
-        assert r <= max(1e-4, 3 * own), (name, r, own)
+        tol_check(f"head_bwd[{B},{edge}].g_{name}", r, 1e-4, own)
     # clamp: zero gradient for s < min_s (camera.py:463)
     small = cam[:, 0] < 0.1
     assert (got[2].cpu()[small, 0] == 0).all()
@@ -123,7 +124,8 @@ def test_rot6d_free_functions(dev, golden_dir, layout, ofn, gkey):
     (gxo,) = torch.autograd.grad((Ro * w.double()).sum(), xo)
     well = slice(0, 56)   # rows 56..59 are nearly parallel pairs in the contiguous layouts: fp32 itself is ill-conditioned there
     own = rel(ofn(x), Ro.detach())   # the fp32 reference's own distance from fp64
-    assert R.shape == (64, 3, 3) and rel(R[well], Ro.detach()[well]) <= 1e-5 and rel(R, Ro.detach()) <= max(1e-5, 3 * own)
+    assert R.shape == (64, 3, 3) and rel(R[well], Ro.detach()[well]) <= 1e-5
+    tol_check(f"rot6d[{layout}].R_all_rows", rel(R, Ro.detach()), 1e-5, own)
     assert rel(gx[well], gxo[well]) <= 1e-4
     if gkey:
         assert rel(R[well], torch.from_numpy(d[f"R_{gkey}"])[well]) <= 1e-6

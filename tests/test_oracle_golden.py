@@ -4,7 +4,9 @@ import os
 import numpy as np
 import torch
 
-from hands_b200.synthetic import synthetic_pcl_inputs
+import pytest
+
+from hands_b200.synthetic import synthetic_head_inputs, synthetic_mano_buffers, synthetic_pcl_inputs
 from oracle import geometry_oracle as O
 
 
@@ -137,3 +139,69 @@ def test_kpe_features_match_reference(golden_dir):
     L = int(d["L"])
     assert torch.equal(O.kpe_pos_enc(center, L), torch.from_numpy(d["center_enc"]))
     assert torch.equal(O.kpe_pos_enc(corner, L), torch.from_numpy(d["corner_enc"]))
+
+
+def test_mesh_constants_match_reference(golden_dir):
+    """a21: the PRODUCT's wrist-seal table and `seal_mano_mesh` (hands_b200/common/body_models.py) and the oracle's, against
+    the reference's own table and function (common/body_models.py:35-72, exec'd by make_golden.py).  Bit-exact: indices."""
+    from hands_b200.common import body_models as P
+
+    g = _load(golden_dir, "mesh_constants.npz")
+    assert np.array_equal(np.asarray(P.SEAL_FACES_R, dtype=np.int64), g["SEAL_FACES_R"])
+    assert np.array_equal(np.asarray(P.CIRCLE_V_ID, dtype=np.int64), g["CIRCLE_V_ID"])
+    v3d, faces = torch.from_numpy(g["v3d"]), torch.from_numpy(g["faces"])
+    for name, is_rhand in (("r", True), ("l", False)):
+        for impl in (P.seal_mano_mesh, O.seal_mano_mesh):
+            sv, sf = impl(v3d, faces, is_rhand)
+            assert sv.shape == (3, 779, 3) and sf.shape == (1554, 3) and sf.dtype == torch.int64
+            assert torch.equal(sf, torch.from_numpy(g[f"sealed_f_{name}"]))
+            assert torch.equal(sv, torch.from_numpy(g[f"sealed_v_{name}"]))
+
+
+def test_mano_head_chain_matches_reference_source(golden_dir):
+    """a11: the oracle's head chain against the reference's OWN MANOHead.forward source (mano_head.py:21-65) run over the same
+    MANO layer (make_golden.py::golden_mano_head_reference_source) -- outputs and gradients to 1e-6 relative."""
+    g = _load(golden_dir, "mano_head_ref.npz")
+    for name, is_rhand in (("r", True), ("l", False)):
+        rotmat, betas, cam, K = synthetic_head_inputs(12, seed=int(g[f"seed_{name}"]), small_s_frac=0.25)
+        buf = synthetic_mano_buffers(is_rhand)
+        r, b, c = rotmat.clone().requires_grad_(True), betas.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+        out = O.mano_head_forward(buf, r, b, c, K, 224.0, 0.1)
+        for k in ["cam_t", "joints3d", "vertices", "j3d.cam", "v3d.cam", "j2d.norm", "pose", "beta", "cam_t.wp"]:
+            ref = torch.from_numpy(g[f"{k}_{name}"])   # (torch's matmul blocking depends on the thread count: not always bit-equal)
+            assert float((out[k].detach() - ref).abs().max()) <= 1e-6 * float(ref.abs().max()), k
+        loss = sum((out[k] * torch.from_numpy(g[f"w_{k}_{name}"])).sum() for k in ("v3d.cam", "j3d.cam", "j2d.norm"))
+        grads = torch.autograd.grad(loss, (r, b, c))
+        for gname, got in zip(("g_rotmat", "g_betas", "g_cam"), grads):
+            ref = torch.from_numpy(g[f"{gname}_{name}"])
+            assert float((got - ref).abs().max() / ref.abs().max()) <= 1e-6, gname
+        aa = torch.from_numpy(g[f"aa_{name}"])
+        out2 = O.mano_head_forward(buf, aa, betas, cam, K, 224.0, 0.1)
+        assert float((out2["j2d.norm"] - torch.from_numpy(g[f"aa_j2d.norm_{name}"])).abs().max()) <= 1e-6
+        assert float((out2["v3d.cam"] - torch.from_numpy(g[f"aa_v3d.cam_{name}"])).abs().max()) <= 1e-6 * float(out2["v3d.cam"].abs().max())
+
+
+def test_mano_layer_state_dict_is_smplx_shaped():
+    """Strict checkpoint exchange with the reference (common/abstract_pl.py:42-44 loads strictly): the drop-in's persistent
+    keys are the smplx.MANO(use_pca=False) set [smplx-recalled]; helper tensors that differ between smplx versions are tolerated;
+    anything else is still an error.  Copies / pickles of a module never carry the device handle cache."""
+    import copy
+    import pickle
+
+    from hands_b200.common.body_models import build_mano_aa
+
+    m = build_mano_aa(True, synthetic=True)
+    assert sorted(m.state_dict().keys()) == sorted([
+        "J_regressor", "betas", "faces_tensor", "global_orient", "hand_mean", "hand_pose", "lbs_weights", "parents", "pose_mean",
+        "posedirs", "shapedirs", "v_template", "vertex_joint_selector.extra_joints_idxs"])
+    assert m.tip_ids.tolist() == [744, 320, 443, 554, 671]
+    sd = dict(m.state_dict())
+    sd["body_pose"] = torch.zeros(1, 3)
+    del sd["hand_mean"]
+    m2 = copy.deepcopy(m)
+    m2.load_state_dict(sd, strict=True)
+    sd["not_a_mano_key"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict(sd, strict=True)
+    m._handles[("cuda", 0)] = ("stamp", object())     # stand-in for a live device handle
+    assert pickle.loads(pickle.dumps(m))._handles == {} and copy.deepcopy(m)._handles == {}
