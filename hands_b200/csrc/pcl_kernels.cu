@@ -337,6 +337,355 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
   }
 }
 
+// ---- forward, default ("fast") form -----------------------------------------------------------------
+// Same decomposition and the same sample positions as pcl_fwd_kernel (the reference's rounding sequence
+// X/(1e-8+Z) -> /R -> *2-1 -> un-normalise is kept, because its -1/+1 steps quantise the position to ~7e-6 px and a
+// white-noise image amplifies any other choice past 1e-5), but with fewer instructions per pixel:
+//   * both IEEE divisions share one refined reciprocal (MUFU.RCP + one Newton step, then Markstein's q + r*y correction);
+//   * position and gather are one pass (no round trip of the positions through shared memory); taps are clamped into the
+//     image and their WEIGHTS masked, so the twelve loads are unconditional;
+//   * the resize is evaluated separably: the two live intermediate rows are interpolated horizontally once per row change
+//     (3 FMUL + 3 FMA) and every output pixel is 3 FMUL + 3 FMA instead of 4 weight products + 16 FMAs.  This is the only
+//     arithmetic difference from torch's kernel (which forms the four 2-D weights first): a few ulp of the output value.
+//   * SrcT = uint8_t: the source image is the data loader's 8-bit image; (u/255 - mean)/std (torchvision Normalize as the
+//     reference applies it, hands_light_dataset.py:177-184) is a 256-entry table per channel built once per CTA, so the
+//     staged tile is a quarter of the bytes and the PCIe copy of the step's images shrinks fourfold.
+// HB_PCL_EXACT=1 / hb_pcl_set_exact(1) selects pcl_fwd_kernel (bit-identical to torch on > 99.9 % of the pixels).
+struct PclNorm { float mean[4]; float std[4]; };
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// a / b given y ~ RN(1/b): q = RN(a*y), r = a - b*q (exact by FMA), RN(q + r*y)
+__device__ __forceinline__ float div_refined(float a, float b, float y) {
+  const float q = __fmul_rn(a, y);
+  const float r = fmaf(-b, q, a);
+  return fmaf(r, y, q);
+}
+
+__device__ __forceinline__ void sample_pos_uv(const Crop& c, float u, float v, float R, float rcpR, float& ix, float& iy) {
+  const float X = __fadd_rn(fmaf(c.P[1], v, __fmul_rn(c.P[0], u)), c.P[2]);
+  const float Y = __fadd_rn(fmaf(c.P[4], v, __fmul_rn(c.P[3], u)), c.P[5]);
+  const float Z = __fadd_rn(fmaf(c.P[7], v, __fmul_rn(c.P[6], u)), c.P[8]);
+  const float den = __fadd_rn(1e-8f, Z);
+  float y = rcp_approx(den);
+  y = fmaf(fmaf(-den, y, 1.0f), y, y);   // one Newton step: y == RN(1/den) except in rare half-way cases
+  const float gx = fmaf(div_by_const(div_refined(X, den, y), R, rcpR), 2.0f, -1.0f);
+  const float gy = fmaf(div_by_const(div_refined(Y, den, y), R, rcpR), 2.0f, -1.0f);
+  const float half = R * 0.5f;
+  ix = fmaf(__fadd_rn(gx, 1.0f), half, -0.5f);
+  iy = fmaf(__fadd_rn(gy, 1.0f), half, -0.5f);
+}
+
+// global-memory tap for the un-staged fallback (fp32 image, or 8-bit image through the normalisation table)
+__device__ __forceinline__ float src_ldg(const float* p, const float*) { return __ldg(p); }
+__device__ __forceinline__ float src_ldg(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
+
+// bilinear gather of one pixel straight from global memory with zero padding (fallback of the fast kernel)
+template <int C, typename SrcT>
+__device__ __forceinline__ void gather_global(const SrcT* __restrict__ src, const float* lut, int R, int plane, float ix, float iy, float* v) {
+  const float Rf = (float)R;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) v[ch] = 0.0f;
+  if (!(ix > -1.0f && ix < Rf && iy > -1.0f && iy < Rf)) return;
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+  const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+  const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+  const bool xa = x0 >= 0, xb = x0 + 1 < R, ya = y0 >= 0, yb = y0 + 1 < R;
+  const SrcT* pl = src + y0 * R + x0;
+#pragma unroll
+  for (int ch = 0; ch < C; ++ch) {
+    const float* lc = lut + (sizeof(SrcT) == 1 ? ch * 256 : 0);
+    const float nw = (xa && ya) ? src_ldg(pl, lc) : 0.0f;
+    const float ne = (xb && ya) ? src_ldg(pl + 1, lc) : 0.0f;
+    const float sw = (xa && yb) ? src_ldg(pl + R, lc) : 0.0f;
+    const float se = (xb && yb) ? src_ldg(pl + R + 1, lc) : 0.0f;
+    float acc = __fmul_rn(nw, wnw);
+    acc = fmaf(ne, wne, acc);
+    acc = fmaf(sw, wsw, acc);
+    acc = fmaf(se, wse, acc);
+    v[ch] = acc;
+    pl += plane;
+  }
+}
+
+constexpr int PCL_TV = 40;   // rows of the per-sub-block linspace table (an intermediate band never has more: 16 * scale + 3, scale <= 1)
+
+template <int C, int RT, typename SrcT, bool V2>   // V2: out is 8-byte aligned and R even -> 64-bit stores
+__global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT* __restrict__ img, const float* __restrict__ params, int crops_per_img, int R_arg,
+                                                                      float* __restrict__ out, int smem_bytes, int tma_ok, PclNorm nrm) {
+  const int R = RT ? RT : R_arg;
+  constexpr bool U8 = sizeof(SrcT) == 1;
+  extern __shared__ __align__(16) float4 mid4[];  // [nrows][s] pixels, channels in .x .y .z .w; then the staged source tile (fp32)
+  __shared__ int reg[6];
+  __shared__ float4 rowrec[PCL_TR];
+  __shared__ uint64_t src_bar;
+  __shared__ float lut[U8 ? C * 256 : 1];
+  __shared__ float tu[RT ? RT : 1];        // linspace(0,1,s) of the crop's columns (compile-time resolution only)
+  __shared__ float tv[RT ? PCL_TV : 1];    // ... and of the sub-block's intermediate rows
+  __shared__ float2 coltab[RT ? RT : 1];   // per output column: (weight of the upper tap, lower tap index) of the horizontal resize
+  const int q = blockIdx.y;
+  const Crop c = load_crop(params + (size_t)q * PF);
+  const int s = c.s;
+  const int Y0 = blockIdx.x * PCL_TR;
+  const int Y1 = min(Y0 + PCL_TR, R) - 1;
+  const int plane = R * R;
+  const SrcT* src = img + (size_t)(q / crops_per_img) * C * plane;
+  float* dst = out + (size_t)q * C * plane;
+  const float Rf = (float)R;
+  const float rcpR = __fdiv_rn(1.0f, Rf);
+  const int tid = threadIdx.x;
+  if (U8) {
+    for (int e = tid; e < C * 256; e += PCL_THREADS) {
+      const int ch = e >> 8;
+      lut[e] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(e & 255), 255.0f), nrm.mean[ch]), nrm.std[ch]);
+    }
+  }
+  if (RT) {
+    for (int i = tid; i < s && i < RT; i += PCL_THREADS) tu[i] = lin01(c, i);
+    for (int x = tid; x < RT; x += PCL_THREADS) {
+      int b0, b1;
+      float lx0, lx1;
+      resize_coef(c, x, R, b0, b1, lx0, lx1);
+      coltab[x] = make_float2(lx1, __int_as_float(b0));   // lx0 = 1 - lx1 and b1 = b0 + (b0 < s-1) are recomputed exactly
+    }
+  }
+  int rows_sub = PCL_TR;
+  while (rows_sub > 1 && ((int)ceilf((float)rows_sub * c.scale) + 3) * s * 16 > smem_bytes) rows_sub >>= 1;
+  const bool fits = ((int)ceilf((float)rows_sub * c.scale) + 3) * s * 16 <= smem_bytes;
+  if (s <= R && fits) {
+    if (tid == 0) { mbar_init(&src_bar, 1); mbar_fence_init(); }
+    int nuse = 0;
+    const int q256 = PCL_THREADS / s, r256 = PCL_THREADS - q256 * s;   // idx += 256  <=>  (row += q256, col += r256) with one carry
+    for (int y0 = Y0; y0 <= Y1; y0 += rows_sub) {
+      const int y1 = min(y0 + rows_sub - 1, Y1);
+      int jlo, jhi, t0, t1;
+      float l0, l1;
+      resize_coef(c, y0, R, jlo, t1, l0, l1);
+      resize_coef(c, y1, R, t0, jhi, l0, l1);
+      const int nrows = jhi - jlo + 1;
+      const int n = nrows * s;
+      float* stile = reinterpret_cast<float*>(mid4 + n);   // source tile [C][rows][cols] fp32, cols a multiple of 4
+      if (tid < 32) {
+        // The band's sample positions are the image of a rectangle of the intermediate grid under a homography: a convex
+        // quad whose corner box (+ the bilinear margin) bounds every tap.  The tile spans that box in UNCLAMPED image
+        // coordinates, at most [-1, R]: the parts outside the image are the reference's zero padding, so the gather needs
+        // neither bounds predicates nor clamps.  fp32 images: warp 0 issues one TMA bulk copy per (channel, in-image row).
+        const int lane = tid;
+        float cx = 0.f, cy = 0.f;
+        if (lane < 4) sample_pos_uv(c, lin01(c, (lane & 1) ? s - 1 : 0), lin01(c, (lane >> 1) ? jhi : jlo), Rf, rcpR, cx, cy);
+        float xmn = lane < 4 ? cx : 3.0e38f, xmx = lane < 4 ? cx : -3.0e38f, ymn = lane < 4 ? cy : 3.0e38f, ymx = lane < 4 ? cy : -3.0e38f;
+#pragma unroll
+        for (int m = 1; m < 4; m <<= 1) {
+          xmn = fminf(xmn, __shfl_xor_sync(0xffffffffu, xmn, m)); xmx = fmaxf(xmx, __shfl_xor_sync(0xffffffffu, xmx, m));
+          ymn = fminf(ymn, __shfl_xor_sync(0xffffffffu, ymn, m)); ymx = fmaxf(ymx, __shfl_xor_sync(0xffffffffu, ymx, m));
+        }
+        xmn = __shfl_sync(0xffffffffu, xmn, 0); xmx = __shfl_sync(0xffffffffu, xmx, 0);
+        ymn = __shfl_sync(0xffffffffu, ymn, 0); ymx = __shfl_sync(0xffffffffu, ymx, 0);
+        int use = 0, bx0 = 0, by0 = 0, ncols = 0, nr = 0;
+        if (tma_ok && xmn == xmn && xmx == xmx && ymn == ymn && ymx == ymx && xmx > -2.0f && ymx > -2.0f && xmn < Rf + 1.0f && ymn < Rf + 1.0f) {
+          const int xl = max(-1, (int)floorf(fmaxf(xmn, -4.0f)) - 1), xh = min(R, (int)floorf(fminf(xmx, Rf + 4.0f)) + 2);
+          const int yl = max(-1, (int)floorf(fmaxf(ymn, -4.0f)) - 1), yh = min(R, (int)floorf(fminf(ymx, Rf + 4.0f)) + 2);
+          bx0 = xl & ~3;                      // two's complement: -1 -> -4
+          ncols = (xh - bx0 + 4) & ~3;
+          by0 = yl;
+          nr = yh - yl + 1;
+          use = nr > 0 && ncols > 0 && (size_t)n * 16 + (size_t)C * nr * ncols * 4 <= (size_t)smem_bytes;
+        }
+        const int cx0 = max(bx0, 0), cx1 = min(bx0 + ncols, R);        // in-image column range (multiples of 4)
+        const int ry0 = max(by0, 0), ry1 = min(by0 + nr, R);           // in-image row range
+        const int pad = use && (bx0 < 0 || bx0 + ncols > R || by0 < 0 || by0 + nr > R);
+        if (lane == 0) {
+          reg[0] = bx0; reg[1] = by0; reg[2] = ncols; reg[3] = nr; reg[4] = use; reg[5] = pad;
+          if (use && !U8) mbar_arrive_expect_tx(&src_bar, (uint32_t)(C * (ry1 - ry0) * (cx1 - cx0) * 4));
+        }
+        __syncwarp();
+        if (use && !U8) {
+          const int nrin = ry1 - ry0;
+          for (int k = lane; k < C * nrin; k += 32) {
+            const int ch = k / nrin, r = ry0 + (k - ch * nrin);
+            bulk_g2s(stile + ((size_t)(ch * nr + (r - by0)) * ncols + (cx0 - bx0)),
+                     reinterpret_cast<const float*>(src) + (size_t)ch * plane + (size_t)r * R + cx0, (uint32_t)((cx1 - cx0) * 4), &src_bar);
+          }
+        }
+      }
+      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this sub-block
+        int a0, a1;
+        float ly0, ly1;
+        resize_coef(c, y0 + tid - 32, R, a0, a1, ly0, ly1);
+        rowrec[tid - 32] = make_float4(ly0, ly1, __int_as_float((a0 - jlo) * s), __int_as_float((a1 - jlo) * s));
+      }
+      if (RT && tid >= 64 && tid - 64 < nrows && tid - 64 < PCL_TV) tv[tid - 64] = lin01(c, jlo + tid - 64);
+      __syncthreads();   // region record, row table, linspace tables, barrier init (and the LUT) are visible
+      const int rx0 = reg[0], ry0 = reg[1], rnc = reg[2], rnr = reg[3];
+      const bool tiled = reg[4] != 0;
+      if (tiled && (U8 || reg[5])) {
+        // 8-bit image: the threads stage the tile themselves, 4 pixels per 32-bit load, normalised through the table,
+        // out-of-image groups zero.  fp32 image: only the out-of-image groups are written (the bulk copies fill the rest).
+        const int nc4 = rnc >> 2;
+        const int tot = C * rnr * nc4;
+        const float inv_nc4 = 1.0f / (float)nc4;
+        for (int e = tid; e < tot; e += PCL_THREADS) {
+          const int rowi = fast_div(e, nc4, inv_nc4), c4 = e - rowi * nc4;   // rowi = ch * rnr + r
+          const int ch = rowi / rnr, r = rowi - ch * rnr;
+          const int y = ry0 + r, x = rx0 + 4 * c4;
+          const bool inside = y >= 0 && y < R && x >= 0 && x < R;            // x, R multiples of 4: a group is all in or all out
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (U8) {
+            if (inside) {
+              const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(src) + (size_t)ch * plane + (size_t)y * R + x));
+              const float* lc = lut + ch * 256;
+              val = make_float4(lc[w & 255u], lc[(w >> 8) & 255u], lc[(w >> 16) & 255u], lc[w >> 24]);
+            }
+            reinterpret_cast<float4*>(stile)[e] = val;
+          } else if (!inside) {
+            reinterpret_cast<float4*>(stile)[e] = val;
+          }
+        }
+      }
+      if (tiled) {
+        if (U8) __syncthreads();
+        else { mbar_wait(&src_bar, nuse & 1); ++nuse; if (reg[5]) __syncthreads(); }
+      }
+      // gather: one pass, thread = intermediate pixel
+      {
+        int i = tid, jr = 0;
+        while (i >= s) { i -= s; ++jr; }
+        const float xlo = (float)rx0, xhi = (float)(rx0 + rnc - 1), ylo = (float)ry0, yhi = (float)(ry0 + rnr - 1);
+        const int toff = ry0 * rnc + rx0;
+        const int chs = rnr * rnc;
+        for (int idx = tid; idx < n; idx += PCL_THREADS) {
+          float ix, iy;
+          if (RT) sample_pos_uv(c, tu[i], tv[min(jr, PCL_TV - 1)], Rf, rcpR, ix, iy);
+          else sample_pos_uv(c, lin01(c, i), lin01(c, jlo + jr), Rf, rcpR, ix, iy);
+          float v[4];
+          // both taps of each axis inside the tile?  (float compares: a NaN position fails them and takes the fallback)
+          if (tiled && ix >= xlo && ix < xhi && iy >= ylo && iy < yhi) {
+            const float fx = floorf(ix), fy = floorf(iy);
+            const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+            const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+            const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+            const float* tl = stile + ((int)fy * rnc + (int)fx - toff);
+            const float* tb = tl + rnc;
+            v[3] = 0.0f;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              float acc = __fmul_rn(tl[0], wnw);
+              acc = fmaf(tl[1], wne, acc);
+              acc = fmaf(tb[0], wsw, acc);
+              acc = fmaf(tb[1], wse, acc);
+              v[ch] = acc;
+              tl += chs; tb += chs;
+            }
+#pragma unroll
+            for (int ch = C; ch < 3; ++ch) v[ch] = 0.0f;
+          } else {   // tile not staged (does not fit / unaligned image), position outside the image, or a tap outside the tile
+            gather_global<C, SrcT>(src, lut, R, plane, ix, iy, v);
+          }
+          mid4[idx] = make_float4(v[0], v[1], v[2], v[3]);
+          i += r256; jr += q256;
+          if (i >= s) { i -= s; ++jr; }
+        }
+      }
+      __syncthreads();
+      // separable resize: a thread owns two adjacent output columns of one half of the sub-block's rows
+      {
+        const int nout = y1 - y0 + 1;
+        const int halfrows = (nout + 1) >> 1;
+        const int g = tid >> 7;
+        const int tA = g * halfrows, tB = min(tA + halfrows, nout);
+        for (int x = 2 * (tid & 127); x < R; x += 256) {
+          int b0[2], b1[2];
+          float lx0[2], lx1[2];
+          if (RT) {
+            const float4 ct = *reinterpret_cast<const float4*>(coltab + x);   // x even, R even: both columns in one 16-byte load
+            lx1[0] = ct.x; b0[0] = __float_as_int(ct.y); lx1[1] = ct.z; b0[1] = __float_as_int(ct.w);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { lx0[k] = __fsub_rn(1.0f, lx1[k]); b1[k] = b0[k] + (b0[k] < s - 1 ? 1 : 0); }
+          } else {
+            resize_coef(c, x, R, b0[0], b1[0], lx0[0], lx1[0]);
+            resize_coef(c, min(x + 1, R - 1), R, b0[1], b1[1], lx0[1], lx1[1]);
+          }
+          int cur0 = -1, cur1 = -1;
+          float h0[2][4], h1[2][4];
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) { h0[k][ch] = 0.f; h1[k][ch] = 0.f; }
+          auto hrow = [&](int o, float (*h)[4]) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float4 a = mid4[o + b0[k]], b = mid4[o + b1[k]];
+              h[k][0] = fmaf(lx1[k], b.x, __fmul_rn(lx0[k], a.x));
+              if (C > 1) h[k][1] = fmaf(lx1[k], b.y, __fmul_rn(lx0[k], a.y));
+              if (C > 2) h[k][2] = fmaf(lx1[k], b.z, __fmul_rn(lx0[k], a.z));
+              if (C > 3) h[k][3] = fmaf(lx1[k], b.w, __fmul_rn(lx0[k], a.w));
+            }
+          };
+          float* op = dst + (size_t)(y0 + tA) * R + x;
+          const bool two = x + 1 < R;
+#pragma unroll 1
+          for (int t = tA; t < tB; ++t, op += R) {
+            const float4 rr = rowrec[t];
+            const int o0r = __float_as_int(rr.z), o1r = __float_as_int(rr.w);
+            if (o0r != cur0) {   // uniform across the row group
+              if (o0r == cur1) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+#pragma unroll
+                  for (int ch = 0; ch < C; ++ch) h0[k][ch] = h1[k][ch];
+              } else hrow(o0r, h0);
+              cur0 = o0r;
+            }
+            if (o1r != cur1) { hrow(o1r, h1); cur1 = o1r; }
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+              const float oa = fmaf(rr.y, h1[0][ch], __fmul_rn(rr.x, h0[0][ch]));
+              const float ob = fmaf(rr.y, h1[1][ch], __fmul_rn(rr.x, h0[1][ch]));
+              if (V2) __stcs(reinterpret_cast<float2*>(op + ch * plane), make_float2(oa, ob));
+              else { __stcs(op + ch * plane, oa); if (two) __stcs(op + ch * plane + 1, ob); }
+            }
+          }
+        }
+      }
+      __syncthreads();   // end of the sub-block: the tile, the tables and the region record are reused
+    }
+    return;
+  }
+  // generic path (s > R, or an intermediate row that does not fit): the four intermediate pixels of every output pixel directly
+  if (U8) __syncthreads();
+  const int npix = (Y1 - Y0 + 1) * R;
+  for (int idx = tid; idx < npix; idx += PCL_THREADS) {
+    const int yy = idx / R, x = idx - yy * R;
+    const int y = Y0 + yy;
+    int a0, a1, b0, b1;
+    float ly0, ly1, lx0, lx1;
+    resize_coef(c, y, R, a0, a1, ly0, ly1);
+    resize_coef(c, x, R, b0, b1, lx0, lx1);
+    const float w00 = __fmul_rn(ly0, lx0), w01 = __fmul_rn(ly0, lx1), w10 = __fmul_rn(ly1, lx0), w11 = __fmul_rn(ly1, lx1);
+    float px[4], py[4], t[4][4];
+    sample_pos(c, a0, b0, Rf, rcpR, px[0], py[0]);
+    sample_pos(c, a0, b1, Rf, rcpR, px[1], py[1]);
+    sample_pos(c, a1, b0, Rf, rcpR, px[2], py[2]);
+    sample_pos(c, a1, b1, Rf, rcpR, px[3], py[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gather_global<C, SrcT>(src, lut, R, plane, px[k], py[k], t[k]);
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+      float acc = __fmul_rn(w01, t[1][ch]);
+      acc = fmaf(w00, t[0][ch], acc);
+      acc = fmaf(w10, t[2][ch], acc);
+      acc = fmaf(w11, t[3][ch], acc);
+      dst[((size_t)ch * R + y) * R + x] = acc;
+    }
+  }
+}
+
 // ---- backward -------------------------------------------------------------------------------------
 // Chunk workspace, per crop (offset params[21], in floats, a multiple of 4): G float4[s*s] intermediate
 // gradient (channels in x,y,z,w); 4*s*s floats per crop.  (Sample positions are recomputed by the consumer.)
@@ -936,39 +1285,75 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
 
 using namespace hb;
 
-template <int C>
-static int launch_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int R, float* out, cudaStream_t st) {
-  const int max_rows = PCL_TR + 2;
+static int g_pcl_exact = -1;   // -1: not decided yet (env HB_PCL_EXACT, default 0 = fast forward)
+static int pcl_exact() {
+  if (g_pcl_exact < 0) { const char* e = getenv("HB_PCL_EXACT"); g_pcl_exact = (e && e[0] == '1') ? 1 : 0; }
+  return g_pcl_exact;
+}
+extern "C" int hb_pcl_set_exact(int on) { const int prev = pcl_exact(); g_pcl_exact = on ? 1 : 0; return prev; }
+
+template <int C, typename SrcT>
+static int launch_fwd(const SrcT* img, const float* params, int n_crops, int crops_per_img, int R, float* out, const PclNorm& nrm, cudaStream_t st) {
+  constexpr bool U8 = sizeof(SrcT) == 1;
   // shared-memory budget per CTA: 44 KB -> 5 CTAs/SM (measured on B200: 3.31 ms vs 4.24 ms at 72 KB / 3 CTAs per SM;
-  // the kernel is issue/latency bound, occupancy pays).  One intermediate row must fit: R*16 bytes * 4 rows.
-  size_t smem = 44 * 1024;
+  // the kernel is issue/latency bound, occupancy pays).  One intermediate row must fit: R*16 bytes * 4 rows.  The 8-bit
+  // variant keeps its normalisation table (C KB) in static shared memory on top.
+  size_t smem = (pcl_exact() && !U8 ? 44 : (U8 ? 41 - C : 41)) * 1024;   // the fast kernel keeps ~3 KB of tables in static shared memory
   { const char* e = getenv("HB_PCL_FWD_SMEM_KB"); if (e) smem = (size_t)atoi(e) * 1024; }   // experiment knob
   if (smem < (size_t)R * 16 * 4) smem = (size_t)R * 16 * 4;
   if (smem > 200 * 1024) { set_error("hb_pcl_fwd: img_res too large for the staged kernel"); return HB_E_UNSUPPORTED; }
-  // bulk copies need 16-byte aligned row segments: R % 4 == 0 and a 16-byte aligned image
+  // bulk copies need 16-byte aligned row segments: R % 4 == 0 (R % 16 for 8-bit images) and a 16-byte aligned image
   static int want_tma = -1;
   if (want_tma < 0) { const char* e = getenv("HB_PCL_TMA"); want_tma = (e && e[0] == '0') ? 0 : 1; }
-  const int tma_ok = want_tma && (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
-  auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
-  HB_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tma_ok = want_tma && (R % (U8 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
   dim3 grid((R + PCL_TR - 1) / PCL_TR, n_crops);
-  fwd_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, max_rows, (int)smem, tma_ok);
+  if constexpr (!U8) {
+    if (pcl_exact()) {
+      auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
+      HB_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fwd_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, PCL_TR + 2, (int)smem, tma_ok);
+      g_launches++;
+      return check_launch("pcl_fwd_kernel");
+    }
+  }
+  const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
+  auto fast_kernel = (R == 224 && v2) ? pcl_fwd_fast_kernel<C, 224, SrcT, true> : (v2 ? pcl_fwd_fast_kernel<C, 0, SrcT, true> : pcl_fwd_fast_kernel<C, 0, SrcT, false>);
+  HB_CUDA(cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fast_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, (int)smem, tma_ok, nrm);
   g_launches++;
-  return check_launch("pcl_fwd_kernel");
+  return check_launch("pcl_fwd_fast_kernel");
 }
 
-extern "C" int hb_pcl_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int C, int img_res, float* out, void* stream) {
+template <typename SrcT>
+static int pcl_fwd_dispatch(const SrcT* img, const float* params, int n_crops, int crops_per_img, int C, int img_res, float* out, const PclNorm& nrm, void* stream) {
   if (n_crops < 0 || crops_per_img <= 0 || C <= 0 || C > 4 || img_res <= 0 || (n_crops > 0 && (!img || !params || !out)) || n_crops % crops_per_img) {
     set_error("hb_pcl_fwd: bad argument (1 <= C <= 4)"); return HB_E_ARG;
   }
   if (n_crops == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (C) {
-    case 1: return launch_fwd<1>(img, params, n_crops, crops_per_img, img_res, out, st);
-    case 2: return launch_fwd<2>(img, params, n_crops, crops_per_img, img_res, out, st);
-    case 3: return launch_fwd<3>(img, params, n_crops, crops_per_img, img_res, out, st);
-    default: return launch_fwd<4>(img, params, n_crops, crops_per_img, img_res, out, st);
+    case 1: return launch_fwd<1, SrcT>(img, params, n_crops, crops_per_img, img_res, out, nrm, st);
+    case 2: return launch_fwd<2, SrcT>(img, params, n_crops, crops_per_img, img_res, out, nrm, st);
+    case 3: return launch_fwd<3, SrcT>(img, params, n_crops, crops_per_img, img_res, out, nrm, st);
+    default: return launch_fwd<4, SrcT>(img, params, n_crops, crops_per_img, img_res, out, nrm, st);
   }
+}
+
+extern "C" int hb_pcl_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int C, int img_res, float* out, void* stream) {
+  PclNorm nrm{};
+  return pcl_fwd_dispatch<float>(img, params, n_crops, crops_per_img, C, img_res, out, nrm, stream);
+}
+
+extern "C" int hb_pcl_fwd_u8(const uint8_t* img, const float* mean_host, const float* std_host, const float* params, int n_crops, int crops_per_img,
+                             int C, int img_res, float* out, void* stream) {
+  if (!mean_host || !std_host || C <= 0 || C > 4) { set_error("hb_pcl_fwd_u8: bad argument (mean/std are C host floats, 1 <= C <= 4)"); return HB_E_ARG; }
+  PclNorm nrm{};
+  for (int ch = 0; ch < C; ++ch) {
+    nrm.mean[ch] = mean_host[ch];
+    nrm.std[ch] = std_host[ch];
+    if (!(std_host[ch] != 0.0f)) { set_error("hb_pcl_fwd_u8: std[%d] must be non-zero", ch); return HB_E_ARG; }
+  }
+  return pcl_fwd_dispatch<uint8_t>(img, params, n_crops, crops_per_img, C, img_res, out, nrm, stream);
 }
 
 // The backward runs in chunks of images: per chunk, pcl_bwd_mid fills the workspace (intermediate gradient +

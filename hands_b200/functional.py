@@ -282,10 +282,19 @@ class PerspectiveCropFunction(torch.autograd.Function):
     Gradient w.r.t. img only (the sampling grid is data)."""
 
     @staticmethod
-    def forward(ctx, img, bbox, K, crops_per_img):
+    def forward(ctx, img, bbox, K, crops_per_img, mean=None, std=None):
         lib = _lib.load()
         needs_grad = bool(img.requires_grad)   # read before _f32c: .contiguous() of a strided image is a new tensor
-        img = _f32c(img, "img")
+        u8 = isinstance(img, torch.Tensor) and img.dtype == torch.uint8
+        if u8:
+            # the data loader's 8-bit image: (u/255 - mean)/std (hands_light_dataset.py:177-184) is fused into the gather
+            if not img.is_cuda:
+                raise RuntimeError(f"img: hands_b200 has no CPU path; expected a CUDA tensor (got {img.device})")
+            if mean is None or std is None:
+                raise ValueError("a uint8 image needs mean= and std= (the reference's img_norm_mean / img_norm_std)")
+            img = img.contiguous()
+        else:
+            img = _f32c(img, "img")
         if img.dim() != 4 or img.shape[2] != img.shape[3]:
             raise ValueError(f"img: expected (B,C,R,R), got {tuple(img.shape)}")
         Bi, C, R, _ = img.shape
@@ -315,7 +324,13 @@ class PerspectiveCropFunction(torch.autograd.Function):
         out = torch.empty(n, C, R, R, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.hb_pcl_setup(_ptr(bbox), _ptr(K), n, R, _ptr(params), _ptr(rot), _stream()), "hb_pcl_setup")
-            _lib.check(lib.hb_pcl_fwd(_ptr(img), _ptr(params), n, crops_per_img, C, R, _ptr(out), _stream()), "hb_pcl_fwd")
+            if u8:
+                m = (ctypes.c_float * C)(*[float(v) for v in mean])
+                sd = (ctypes.c_float * C)(*[float(v) for v in std])
+                _lib.check(lib.hb_pcl_fwd_u8(_ptr(img), ctypes.cast(m, ctypes.c_void_p), ctypes.cast(sd, ctypes.c_void_p), _ptr(params), n,
+                                             crops_per_img, C, R, _ptr(out), _stream()), "hb_pcl_fwd_u8")
+            else:
+                _lib.check(lib.hb_pcl_fwd(_ptr(img), _ptr(params), n, crops_per_img, C, R, _ptr(out), _stream()), "hb_pcl_fwd")
         ctx.save_for_backward(params)
         ctx.dims = (Bi, C, R, crops_per_img)
         ctx.mark_non_differentiable(rot)
@@ -334,4 +349,4 @@ class PerspectiveCropFunction(torch.autograd.Function):
         ws = _workspace(nbytes, dev)
         with torch.cuda.device(dev):
             _lib.check(lib.hb_pcl_bwd(_ptr(g_out), _ptr(params), n, cpi, C, R, _ptr(g_img), _ptr(ws), nbytes, _stream()), "hb_pcl_bwd")
-        return g_img, None, None, None
+        return g_img, None, None, None, None, None

@@ -6,14 +6,18 @@ import torch
 from .functional import PerspectiveCropFunction, RotApplyFunction
 
 
-def perspective_crop(img, bbox_xyxy, K, img_res=224, crops_per_img=1):
+def perspective_crop(img, bbox_xyxy, K, img_res=224, crops_per_img=1, mean=None, std=None):
     """img (Bi,3,img_res,img_res) fp32 CUDA; bbox_xyxy (Bi*crops_per_img,4) int [x0,y0,x1,y1] inside the
     image; K (Bi*crops_per_img,3,3).  Crop c samples image c // crops_per_img.
     Returns crop (Bi*crops_per_img,3,img_res,img_res) and R_virt2orig (Bi*crops_per_img,3,3).
-    Semantics = lines 425-467 of the reference closure; gradient flows to img."""
+    Semantics = lines 425-467 of the reference closure; gradient flows to img.
+
+    Extension: `img` may be the data loader's uint8 image with `mean`/`std` (the reference's img_norm_mean/std, C floats):
+    the normalisation (u/255 - mean)/std the reference applies before the crop (hands_light_dataset.py:177-184) is fused
+    into the gather -- same crops, a quarter of the bytes over PCIe.  No gradient flows to a uint8 image."""
     if img.shape[-1] != img_res or img.shape[-2] != img_res:
         raise ValueError(f"img must be {img_res}x{img_res} (the reference crops from the resized full image)")
-    return PerspectiveCropFunction.apply(img, bbox_xyxy, K, int(crops_per_img))
+    return PerspectiveCropFunction.apply(img, bbox_xyxy, K, int(crops_per_img), mean, std)
 
 
 def apply_virtual_rotation(R_virt2orig, pose):

@@ -25,7 +25,11 @@ NV, NJ, NOJ, NB = 778, 16, 21, 10
 
 
 class GeometryStep:
-    def __init__(self, samples, device, img_res=224, with_pcl=True, with_mano=True, hands_per_sample=2, seed=0, grads_on=("v3d", "j3d", "j2d")):
+    IMG_MEAN = (0.485, 0.456, 0.406)   # the reference's img_norm_mean / img_norm_std (src/parsers/parser.py:45-46)
+    IMG_STD = (0.229, 0.224, 0.225)
+
+    def __init__(self, samples, device, img_res=224, with_pcl=True, with_mano=True, hands_per_sample=2, seed=0, grads_on=("v3d", "j3d", "j2d"),
+                 src_u8=False):
         self.lib = _lib.load()
         self.S, self.dev, self.R = int(samples), torch.device(device), int(img_res)
         self.with_pcl, self.with_mano, self.hps = with_pcl, with_mano, hands_per_sample
@@ -46,7 +50,13 @@ class GeometryStep:
             _, bbox, Kc = synthetic_pcl_inputs(n, seed=seed, img_res=R, smin=R // 4, smax=3 * R // 4)
             self.bbox = bbox.to(dev)
             self.Kcrop = Kc.to(dev)
-            self.img = torch.randn(S, 3, R, R, generator=gen, **f32)
+            self.src_u8 = bool(src_u8)
+            if self.src_u8:   # the data loader's 8-bit image; normalisation fused into the crop forward (hb_pcl_fwd_u8)
+                self.img = torch.randint(0, 256, (S, 3, R, R), generator=gen, device=dev, dtype=torch.uint8)
+                self._mean = (ctypes.c_float * 3)(*self.IMG_MEAN)
+                self._std = (ctypes.c_float * 3)(*self.IMG_STD)
+            else:
+                self.img = torch.randn(S, 3, R, R, generator=gen, **f32)
             self.crops = torch.empty(n, 3, R, R, **f32)
             self.g_crops = torch.randn(n, 3, R, R, generator=gen, **f32)
             self.g_img = torch.empty(S, 3, R, R, **f32)
@@ -90,6 +100,10 @@ class GeometryStep:
         _lib.check(self.lib.hb_pcl_setup(_ptr(self.bbox), _ptr(self.Kcrop), self.n, self.R, _ptr(self.params), _ptr(self.rot), self._st()), "hb_pcl_setup")
 
     def pcl_forward(self):
+        if self.src_u8:
+            _lib.check(self.lib.hb_pcl_fwd_u8(_ptr(self.img), ctypes.cast(self._mean, ctypes.c_void_p), ctypes.cast(self._std, ctypes.c_void_p), _ptr(self.params),
+                                              self.n, self.hps, 3, self.R, _ptr(self.crops), self._st()), "hb_pcl_fwd_u8")
+            return
         _lib.check(self.lib.hb_pcl_fwd(_ptr(self.img), _ptr(self.params), self.n, self.hps, 3, self.R, _ptr(self.crops), self._st()), "hb_pcl_fwd")
 
     def pcl_backward(self):

@@ -186,6 +186,18 @@ int hb_pcl_homography_host(const int32_t* bbox_host, const float* K_host, int im
  *   interpolate(bilinear, align_corners=True) to R x R, fused. out (n_crops, C, R, R). */
 int hb_pcl_fwd(const float* img, const float* params, int n_crops, int crops_per_img, int C, int img_res,
                float* out, void* stream);
+/* Forward arithmetic mode: 0 (default) = same sample positions as the reference's fp32 chain, resize evaluated separably
+ *   (differs from torch's kernel by a few ulp of the output); 1 = torch's CPU operation order reproduced exactly
+ *   (bit-identical on > 99.9 % of the pixels, ~1.3x the instructions).  Environment HB_PCL_EXACT sets the initial value.
+ *   Returns the previous setting.  Process-wide. */
+int hb_pcl_set_exact(int on);
+/* Same crop from the data loader's 8-bit image (n_crops/crops_per_img, C, R, R) uint8: x = (u/255 - mean[c]) / std[c]
+ *   (torchvision Normalize as the reference applies it to the full image, src/datasets/hands_light_dataset.py:177-184)
+ *   is fused into the gather, so the result equals hb_pcl_fwd on the normalised fp32 image while a quarter of the bytes
+ *   cross PCIe / HBM.  mean_host, std_host: C floats on the HOST.  hb_pcl_bwd is unchanged (gradient w.r.t. the normalised
+ *   image). */
+int hb_pcl_fwd_u8(const uint8_t* img, const float* mean_host, const float* std_host, const float* params, int n_crops,
+                  int crops_per_img, int C, int img_res, float* out, void* stream);
 /* Backward w.r.t. img (the grid is data).  Domain: boxes no larger than the image (s <= img_res), which the reference
  * guarantees by clipping boxes to the image (common/data_utils.py:508); a larger crop contributes no gradient here and
  * the Python wrapper rejects it up front.  g_out (n_crops,C,R,R) -> g_img (n_crops/crops_per_img,C,R,R),

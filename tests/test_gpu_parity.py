@@ -374,7 +374,37 @@ def test_free_functions_against_golden(dev, golden_dir):
     assert (data_utils.unormalize_kp2d(j2d_n.detach(), 224).cpu() - torch.from_numpy(c["j2d_un"])).abs().max() < 1e-3
 
 
-def test_pcl_forward_against_golden(dev, golden_dir):
+@pytest.fixture
+def pcl_exact_mode():
+    """torch's CPU operation order reproduced exactly (HB_PCL_EXACT=1): the mode the bit-level golden comparison runs in."""
+    from hands_b200 import _lib
+
+    prev = _lib.load().hb_pcl_set_exact(1)
+    yield
+    _lib.load().hb_pcl_set_exact(prev)
+
+
+def test_pcl_forward_against_golden_default_mode(dev, golden_dir):
+    """The reference's own crops (golden) against the DEFAULT forward: 2e-6 of the crop's range."""
+    from hands_b200.pcl import perspective_crop
+
+    g = np.load(os.path.join(golden_dir, "pcl.npz"))
+    img = torch.from_numpy(g["small_img"]).to(dev)
+    bbox = torch.from_numpy(g["small_bbox"].astype(np.int32)).to(dev)
+    K = torch.from_numpy(np.repeat(g["small_K"], 2, axis=0)).float().to(dev)
+    crop, rot = perspective_crop(img, bbox, K, img_res=64, crops_per_img=2)
+    ref = torch.from_numpy(g["small_crop"])
+    assert torch.equal(rot.cpu(), torch.from_numpy(g["small_rot"]))
+    tol_check("pcl_golden_small_default", float((crop.cpu() - ref).abs().max() / ref.abs().max()), 2e-6)
+    img2, bbox2, K2 = synthetic_pcl_inputs(4, seed=int(g["full_seed"]), img_res=224)
+    for j in range(4):
+        b = (j // 2) * 2
+        c2, _ = perspective_crop(img2[b : b + 1].to(dev), bbox2[j : j + 1].to(dev), K2[b : b + 1].to(dev), img_res=224)
+        ref2 = torch.from_numpy(g["full_crop_sub4"][j])
+        tol_check(f"pcl_golden_full_default[{j}]", float((c2[0, :, ::4, ::4].cpu() - ref2).abs().max() / ref2.abs().max()), 2e-6)
+
+
+def test_pcl_forward_against_golden(dev, golden_dir, pcl_exact_mode):
     from hands_b200.pcl import perspective_crop
 
     g = np.load(os.path.join(golden_dir, "pcl.npz"))
@@ -574,3 +604,64 @@ def test_no_cpu_fallback():
 
     with pytest.raises(RuntimeError):
         rot.matrix_to_axis_angle(torch.eye(3)[None])
+
+
+@pytest.mark.parametrize("res,cpi", [(224, 2), (96, 1), (64, 3)])
+def test_pcl_fast_forward_matches_exact_forward(dev, res, cpi):
+    """The default (fast) forward keeps the reference's sample positions and only evaluates the resize separably: a few ulp
+    from the exact-mode forward (which is bit-identical to torch on > 99.9 % of pixels), on white noise."""
+    from hands_b200 import _lib
+    from hands_b200.pcl import perspective_crop
+
+    B = 5
+    n = B * cpi
+    img, bbox, K = synthetic_pcl_inputs(n, seed=res, img_res=res, smin=res // 4, smax=3 * res // 4)
+    img = img[:B].contiguous().to(dev)
+    bbox[0] = torch.tensor([0, 0, 30, 40])                      # touches the top-left image corner: zero-padding border of the tile
+    bbox[1] = torch.tensor([res - 41, res - 31, res - 1, res - 1])   # bottom-right corner
+    bbox[2] = torch.tensor([7, 9, 7, 9])                         # empty box -> s = img_res
+    lib = _lib.load()
+    out = {}
+    prev = lib.hb_pcl_set_exact(0)
+    try:
+        for mode in (0, 1):
+            lib.hb_pcl_set_exact(mode)
+            with torch.no_grad():
+                out[mode], _ = perspective_crop(img, bbox.to(dev), K.to(dev), img_res=res, crops_per_img=cpi)
+    finally:
+        lib.hb_pcl_set_exact(prev)
+    tol_check(f"pcl_fast_vs_exact[{res}]", float((out[0] - out[1]).abs().max() / out[1].abs().max()), 2e-6)
+
+
+@pytest.mark.parametrize("res,cpi", [(224, 2), (96, 1)])
+def test_pcl_uint8_source_matches_normalised_fp32_source(dev, res, cpi):
+    """hb_pcl_fwd_u8: crops of the 8-bit image with the normalisation fused == crops of the normalised fp32 image
+    ((u/255 - mean)/std as torchvision Normalize computes it, hands_light_dataset.py:177-184); and against the oracle."""
+    from hands_b200.pcl import perspective_crop
+
+    B = 4
+    n = B * cpi
+    _, bbox, K = synthetic_pcl_inputs(n, seed=res + 1, img_res=res, smin=res // 4, smax=3 * res // 4)
+    bbox[0] = torch.tensor([0, 0, 50, 33])
+    g = torch.Generator().manual_seed(4)
+    u8 = torch.randint(0, 256, (B, 3, res, res), generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    x = (u8.float() / 255.0 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    with torch.no_grad():
+        c8, r8 = perspective_crop(u8.to(dev), bbox.to(dev), K.to(dev), img_res=res, crops_per_img=cpi, mean=mean, std=std)
+        cf, rf = perspective_crop(x.to(dev), bbox.to(dev), K.to(dev), img_res=res, crops_per_img=cpi)
+    assert torch.equal(r8, rf)
+    tol_check(f"pcl_u8_vs_fp32[{res}]", float((c8 - cf).abs().max() / cf.abs().max()), 1e-6)
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        ref, _ = O.perspective_crop(x.repeat_interleave(cpi, dim=0), bbox, K, res)
+    finally:
+        torch.set_num_threads(nt)
+    tol_check(f"pcl_u8_vs_oracle[{res}]", float((c8.cpu() - ref).abs().max() / ref.abs().max()), 2e-5)
+    with pytest.raises(ValueError):
+        perspective_crop(u8.to(dev), bbox.to(dev), K.to(dev), img_res=res, crops_per_img=cpi)   # mean/std are required
+    with pytest.raises(ValueError, match="inverted"):
+        bad = bbox.clone()
+        bad[1] = torch.tensor([60, 60, 20, 20])
+        perspective_crop(x.to(dev), bad, K.to(dev), img_res=res, crops_per_img=cpi)
