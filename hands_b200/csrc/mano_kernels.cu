@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(Mano
   float* Gv = Vs + HSUB * XS;                          // [HSUB][XS]   dL/dvertex
   float* Gp = Gv + HSUB * XS;                          // [VPB*3][HSUB] dL/dv_posed, hand fastest
   float* Og = Gp + (USE_VP ? 0 : VPB * 3 * HSUB);      // [HSUB][8]    per-hand sums of g_vertices / g_v3d (+ tip joints)
+  float* Ogw = Og + HSUB * 8;                          // [VPB/32][HSUB][8] the same per warp (summed in warp order: deterministic)
   const int tid = threadIdx.x;
   const int g = blockIdx.x, slice = blockIdx.y;
   const int v = slice * VPB + tid;
@@ -403,7 +404,6 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(Mano
 
 #pragma unroll
   for (int sub = 0; sub < HBF / HSUB; ++sub) {
-    if (tid < HSUB * 8) Og[tid] = 0.f;
 #pragma unroll
     for (int hh = 0; hh < HSUB; ++hh) {
       if (USE_VP) {
@@ -487,16 +487,23 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(Mano
       } else {
         Gp[(3 * tid + 0) * GPS + hh] = gp[0]; Gp[(3 * tid + 1) * GPS + hh] = gp[1]; Gp[(3 * tid + 2) * GPS + hh] = gp[2];
       }
-      // per-hand sums -> Og (warp shuffle then one smem atomic per warp)
+      // per-hand sums: warp shuffle tree, one slot per warp; the slots are added in warp order after the barrier (no float
+      // atomics: g_cam / g_transl do not depend on the order the warps arrive in)
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float a1 = s1[k], a2 = s2[k];
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, m); a2 += __shfl_xor_sync(0xffffffffu, a2, m); }
-        if (lane == 0) { atomicAdd(Og + hh * 8 + k, a1); atomicAdd(Og + hh * 8 + 3 + k, a2); }
+        if (lane == 0) { Ogw[((tid >> 5) * HSUB + hh) * 8 + k] = a1; Ogw[((tid >> 5) * HSUB + hh) * 8 + 3 + k] = a2; }
       }
     }
     __syncthreads();
+    if (tid < HSUB * 8 && (tid & 7) < 6) {
+      float t = 0.f;
+#pragma unroll
+      for (int wdx = 0; wdx < VPB / 32; ++wdx) t += Ogw[wdx * HSUB * 8 + tid];
+      Og[tid] = t;
+    } else if (tid < HSUB * 8) Og[tid] = 0.f;
     // ---- phase A: gA[h][j][r][cc] = sum_v W[v][j] gV[v][r] * [v_posed;1][cc]     thread = (hand, joint)
     if (tid < HSUB * NJ) {
       const int hh = tid & (HSUB - 1), j = tid / HSUB;
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(Mano
         ws[ws_gF(B) + (((size_t)slice * G + g) * HBF + h) * FS + tid] = gf[hh];
       }
     }
-    if (tid < HSUB * 8) {
+    if (tid < HSUB * 8) {   // written by this same thread above
       const int hh = tid >> 3, k = tid & 7;
       const int h = sub * HSUB + hh;
       ws[ws_gO(B) + (((size_t)slice * G + g) * HBF + h) * 8 + k] = Og[hh * 8 + k];
@@ -914,8 +921,8 @@ static bool use_tc() {
 
 static const size_t kSkinFwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + HBF * XS);
 static const size_t kSkinFwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + HBF * XS);
-static const size_t kSkinBwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + 2 * HSUB * XS + VPB * 3 * HSUB + HSUB * 8);
-static const size_t kSkinBwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + 2 * HSUB * XS + HSUB * 8);
+static const size_t kSkinBwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + 2 * HSUB * XS + VPB * 3 * HSUB + HSUB * 8 + (VPB / 32) * HSUB * 8);
+static const size_t kSkinBwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + 2 * HSUB * XS + HSUB * 8 + (VPB / 32) * HSUB * 8);
 
 extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
                                 const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
