@@ -93,58 +93,32 @@ WORKLOAD = "C4 two-hand (left+right MANO) + 2 PCL crops/sample sharing one sourc
 
 
 # ------------------------------------------------------------------------------------------------
-class CpuReferenceStep:
-    """Reference torch CPU path for the same step: PCL (grid_sample + interpolate, batched per crop as the
-    reference closure does) + orientation fix-up + MANOHead right/left, forward and backward."""
+def cpu_baseline_variants(samples, steps, warmup, want_pool=True):
+    """The reference torch CPU path (oracle) on the host cores, several ways (scripts/bench_legs.py):
+      per_sample_loop_all_threads   the reference's per-sample crop loop + batched MANO heads, torch intra-op threads = all cores
+      per_sample_loop_1_thread      the same on one thread (bounded to a quarter of the sample)
+      worker_pool                   one single-threaded process per core for the crops (the reference's DataLoader-worker
+                                    parallelism) while the parent runs the MANO heads on all threads
+      batched_fixed_s               ONE grid_sample + ONE interpolate for the batch (only possible at a single box size:
+                                    an upper bound for a batched CPU rewrite, not the reference's code)
+    Returns (best hands/s among the first three, dict)."""
+    from scripts import bench_legs as L
 
-    def __init__(self, samples, seed=0):
-        from hands_b200.synthetic import synthetic_head_inputs, synthetic_mano_buffers, synthetic_pcl_inputs
-        from oracle import geometry_oracle as O
-
-        self.O, self.S = O, samples
-        n = samples * HANDS_PER_SAMPLE
-        g = torch.Generator().manual_seed(seed)
-        _, self.bbox, self.Kc = synthetic_pcl_inputs(n, seed=seed, img_res=IMG_RES, smin=IMG_RES // 4, smax=3 * IMG_RES // 4)
-        self.img = torch.randn(samples, 3, IMG_RES, IMG_RES, generator=g)
-        self.g_crops = torch.randn(n, 3, IMG_RES, IMG_RES, generator=g)
-        self.hands = []
-        for side in range(HANDS_PER_SAMPLE):
-            rotmat, betas, cam, K = synthetic_head_inputs(samples, seed=seed + 10 * side)
-            self.hands.append(dict(buf=synthetic_mano_buffers(side == 0), rotmat=rotmat, betas=betas, cam=cam, K=K,
-                                   g_v3d=torch.randn(samples, 778, 3, generator=g), g_j3d=torch.randn(samples, 21, 3, generator=g),
-                                   g_j2d=torch.randn(samples, 21, 2, generator=g)))
-
-    def run(self):
-        O = self.O
-        img = self.img.clone().requires_grad_(True)
-        src = img.repeat_interleave(HANDS_PER_SAMPLE, dim=0)
-        crops, rot = O.perspective_crop(src, self.bbox, self.Kc, IMG_RES)
-        outs, grads = [crops], [self.g_crops]
-        leaves = [img]
-        rot = rot.view(self.S, HANDS_PER_SAMPLE, 3, 3)
-        for side, h in enumerate(self.hands):
-            r = h["rotmat"].clone().requires_grad_(True)
-            b = h["betas"].clone().requires_grad_(True)
-            c = h["cam"].clone().requires_grad_(True)
-            pose = O.pcl_fix_global_orient(rot[:, side], r)
-            o = O.mano_head_forward(h["buf"], pose, b, c, h["K"], float(IMG_RES), 0.1)
-            outs += [o["v3d.cam"], o["j3d.cam"], o["j2d.norm"]]
-            grads += [h["g_v3d"], h["g_j3d"], h["g_j2d"]]
-            leaves += [r, b, c]
-        torch.autograd.backward(outs, grads)
-        return sum(float(x.grad.sum()) for x in leaves)
-
-
-def time_cpu_reference(samples, steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = CpuReferenceStep(samples)
-    for _ in range(warmup):
-        step.run()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step.run()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return samples * HANDS_PER_SAMPLE / dt, dt
+    cores = os.cpu_count() or 1
+    out = {}
+    v, dt = L.cpu_loop_all_threads(samples, steps, warmup)
+    out["per_sample_loop_all_threads"] = {"value": v, "ms_per_step": dt * 1e3, "cores": cores, "samples": samples}
+    s1 = max(2, samples // 4)
+    v1, dt1 = L.cpu_loop_one_thread(s1)
+    out["per_sample_loop_1_thread"] = {"value": v1, "ms_per_step": dt1 * 1e3, "cores": 1, "samples": s1}
+    if want_pool:
+        r = L.cpu_worker_pool(samples, steps, warmup)
+        if r is not None:
+            out["worker_pool"] = {"value": r[0], "ms_per_step": r[1] * 1e3, "cores": cores, "workers": r[2], "samples": samples}
+    vb, dtb = L.cpu_batched(samples, steps, warmup)
+    out["batched_fixed_s"] = {"value": vb, "ms_per_step": dtb * 1e3, "cores": cores, "samples": samples, "s": 112}
+    best = max((k for k in out if k != "batched_fixed_s"), key=lambda k: out[k]["value"] if k != "per_sample_loop_1_thread" else -1.0)
+    return best, out
 
 
 def cpu_model():
@@ -162,16 +136,18 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     samples = args.ref_samples
-    hps, dt = time_cpu_reference(samples, args.steps, args.warmup)
+    best, var = cpu_baseline_variants(samples, max(1, args.steps), max(1, args.warmup))
+    hps, dt = var[best]["value"], var[best]["ms_per_step"] * 1e-3
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": hps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "arm": "reference torch ops on the host CPU (oracle), bounded sample of the same workload",
+        "config": {"workload": WORKLOAD, "arm": "reference torch ops on the host CPU (oracle), bounded sample of the same workload; best of the "
+                   "all-thread per-sample loop and the one-process-per-core crop workers",
                    "samples_per_step": samples, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES, "bbox_side": "U{56..168}",
                    "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"]},
-        "cpu_baseline": {"value": hps, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model(),
-                         "sample": f"{samples} samples ({samples * HANDS_PER_SAMPLE} hands + crops) per step; oracle/geometry_oracle.py = reference torch ops on CPU, all host threads"},
+        "cpu_baseline": {"value": hps, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model(), "variant": best, "variants": var,
+                         "sample": f"{samples} samples ({samples * HANDS_PER_SAMPLE} hands + crops) per step; oracle/geometry_oracle.py = reference torch ops on CPU"},
         "e2e": {"value": hps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -238,12 +214,15 @@ def run_ours(args, rank, world, local_rank):
         elapsed = float(t.item())
     hands_per_step = S * HANDS_PER_SAMPLE * world
     value = hands_per_step * args.steps / elapsed
+    bytes_per_sample = step.bytes_per_sample()
 
-    # ---- per-kernel timing (each kernel alone on the current stream, CUDA events) for the roofline ------------
-    # One-chunk batch (1024 images = 2048 crops = the launch shape of the backward chunks in the timed step), so one
-    # call == one launch of the kernel in question.
+    # ---- per-family and per-kernel timing (each alone on the current stream, CUDA events) for the roofline ------------
+    # One-chunk batch for the kernels (1024 images = 2048 crops = the launch shape of the backward chunks in the timed
+    # step), so one call == one launch of the kernel in question.  Every leg re-reads inputs far larger than L2.
+    from scripts import bench_legs as L
+
     peak, peak_src = peaks()
-    fam, kern = {}, {}
+    fam, kern, overlap, tf32_peak = {}, {}, {}, None
     if rank == 0:
         n = step.n
         plane = 3 * IMG_RES * IMG_RES * 4
@@ -251,18 +230,23 @@ def run_ours(args, rank, world, local_rank):
         step.pcl_setup()
         t_fwd = cuda_time(step.pcl_forward, reps, 2, dev)
         t_bwd = cuda_time(step.pcl_backward, reps, 2, dev)
-        t_mf = cuda_time(lambda: step.mano_forward(0), reps, 2, dev)
-        t_mb = cuda_time(lambda: step.mano_backward(0), reps, 2, dev)
+        t_mf = cuda_time(lambda: [step.mano_forward(0), step.mano_forward(1)], reps, 2, dev)
+        t_mb = cuda_time(lambda: [step.mano_backward(0), step.mano_backward(1)], reps, 2, dev)
+        t_seq = cuda_time(lambda: step.run(overlap=False), reps, 2, dev)
         b_fwd = n * (plane + 12.0 * step.mean_s2)
         b_bwd = n * plane + S * plane
         fam = {
             "pcl_fwd": {"ms": t_fwd * 1e3, "alg_bytes": b_fwd, "gbs": b_fwd / t_fwd / 1e9, "frac": b_fwd / t_fwd / 1e9 / peak},
             "pcl_bwd (scan + mid + img kernels, all chunks)": {"ms": t_bwd * 1e3, "alg_bytes": b_bwd, "gbs": b_bwd / t_bwd / 1e9, "frac": b_bwd / t_bwd / 1e9 / peak},
-            "mano_fwd (pose + blend_tc + skin)": {"ms": t_mf * 1e3, "alg_bytes": S * 20020.0, "gbs": S * 20020.0 / t_mf / 1e9, "frac": S * 20020.0 / t_mf / 1e9 / peak,
-                                                  "hands_per_s": S / t_mf},
-            "mano_bwd (pose + blend_tc + skin + gfeat_tc + pose)": {"ms": t_mb * 1e3, "alg_bytes": S * 11048.0, "gbs": S * 11048.0 / t_mb / 1e9,
-                                                                    "frac": S * 11048.0 / t_mb / 1e9 / peak, "hands_per_s": S / t_mb},
+            "mano_fwd r+l (pose + blend_tc + skin)": {"ms": t_mf * 1e3, "alg_bytes": 2 * S * 20020.0, "gbs": 2 * S * 20020.0 / t_mf / 1e9,
+                                                      "frac": 2 * S * 20020.0 / t_mf / 1e9 / peak, "hands_per_s": 2 * S / t_mf},
+            "mano_bwd r+l (pose + blend_tc + skin + gfeat_tc + pose)": {"ms": t_mb * 1e3, "alg_bytes": 2 * S * 11048.0, "gbs": 2 * S * 11048.0 / t_mb / 1e9,
+                                                                        "frac": 2 * S * 11048.0 / t_mb / 1e9 / peak, "hands_per_s": 2 * S / t_mb},
         }
+        fused_ms = elapsed / args.steps * 1e3
+        overlap = {"fused_ms": fused_ms, "single_stream_ms": t_seq * 1e3, "sum_of_families_ms": (t_fwd + t_bwd + t_mf + t_mb) * 1e3,
+                   "pcl_alone_ms": (t_fwd + t_bwd) * 1e3, "mano_alone_ms": (t_mf + t_mb) * 1e3,
+                   "mano_exposed_ms": fused_ms - (t_fwd + t_bwd) * 1e3}
         Sk = min(S, 1024)
         ks = step if S == Sk else GeometryStep(Sk, dev, img_res=IMG_RES, seed=7)
         ks.pcl_setup()
@@ -271,23 +255,48 @@ def run_ours(args, rank, world, local_rank):
         tk_fwd = cuda_time(ks.pcl_forward, reps, 2, dev)
         tk_mid = cuda_time(lambda: ks.pcl_backward_stage(1), reps, 2, dev)
         tk_img = cuda_time(lambda: ks.pcl_backward_stage(2), reps, 2, dev)
-        traffic = {}
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
-                traffic = json.load(fh)
-        except Exception:
-            pass
+        traffic, traffic_src = {}, None
+        for name in ("traffic_r2.json", "traffic_r1.json"):   # dram bytes per launch from the committed `ncu --set full` captures
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as fh:
+                    traffic, traffic_src = json.load(fh), "profiles/" + name
+                break
+            except Exception:
+                pass
         ab = {"pcl_fwd_kernel": ks.n * (plane + 12.0 * ks.mean_s2), "pcl_bwd_mid_kernel": ks.n * plane, "pcl_bwd_img_kernel": Sk * plane}
         tt = {"pcl_fwd_kernel": tk_fwd, "pcl_bwd_mid_kernel": tk_mid, "pcl_bwd_img_kernel": tk_img}
         for name in ab:
             kern[name] = {"us_per_launch": tt[name] * 1e6, "alg_bytes_per_launch": ab[name], "achieved": ab[name] / tt[name] / 1e9,
-                          "frac": ab[name] / tt[name] / 1e9 / peak, "traffic": next((v for k, v in traffic.items() if k.startswith(name[:-len("_kernel")])), None), "crops_per_launch": ks.n}
+                          "frac": ab[name] / tt[name] / 1e9 / peak, "traffic": next((v for k, v in traffic.items() if k.startswith(name[:-len("_kernel")])), None),
+                          "crops_per_launch": ks.n}
         del ks
+        try:
+            tf32_peak = L.measure_tf32_peak(dev)
+        except Exception:
+            tf32_peak = None
 
     # ---- e2e: host buffers, copies inside the timed region ---------------------------------------------
-    e2e = None
+    e2e = e2e_f32 = None
     if not args.no_e2e:
-        e2e = run_e2e(step, args, dev, world, barrier)
+        e2e = run_e2e(step, args, dev, world, barrier, src_u8=True)
+        if world == 1 and not args.quick:
+            e2e_f32 = run_e2e(step, args, dev, world, barrier, src_u8=False, steps=2)
+
+    # ---- the other BASELINE.json configs + the autograd-API path (sub-results, not the headline) ---------
+    configs = {}
+    if not args.quick:
+        if world > 1:
+            configs["C5"] = L_c5(dev, world, rank, args)
+            if S * world != 65536 and 65536 % world == 0 and 65536 // world <= 32768:
+                configs["C4_true_shard"] = c4_true_shard(dev, world, rank, 65536 // world, barrier, args)
+        if rank == 0 and world == 1:
+            del step
+            torch.cuda.empty_cache()
+            step = None
+            configs["C1"] = L.config_c1()
+            configs["C2"] = L.config_c2(dev, peak, tf32_peak)
+            configs["C3"] = L.config_c3(dev, peak)
+            configs["api_autograd"] = L.autograd_api(dev)
 
     if rank != 0:
         return
@@ -296,7 +305,10 @@ def run_ours(args, rank, world, local_rank):
     share = {"pcl_fwd_kernel": fam["pcl_fwd"]["ms"], "pcl_bwd_mid_kernel": kern["pcl_bwd_mid_kernel"]["us_per_launch"] * 1e-3 * chunks,
              "pcl_bwd_img_kernel": kern["pcl_bwd_img_kernel"]["us_per_launch"] * 1e-3 * chunks}
     dom = max(share, key=share.get)
-    step_bytes = step.bytes_per_sample() * S
+    bps = bytes_per_sample
+    step_bytes = bps * S
+    step_gbs = value / world / HANDS_PER_SAMPLE * bps / 1e9
+    mano_hps = 2 * S / ((fam["mano_fwd r+l (pose + blend_tc + skin)"]["ms"] + fam["mano_bwd r+l (pose + blend_tc + skin + gfeat_tc + pose)"]["ms"]) * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -306,26 +318,73 @@ def run_ours(args, rank, world, local_rank):
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
                    "streams": "pcl || mano" if not args.no_overlap else "single",
+                   "pcl_forward": "exact (torch op order)" if os.environ.get("HB_PCL_EXACT", "0") == "1" else "default (reference sample positions, separable resize)",
                    "mano_contractions": "tcgen05 3xTF32" if os.environ.get("HB_MANO_TC", "1") != "0" else "ffma"},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": e2e,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
-                     "traffic": kern[dom]["traffic"], "peak_source": peak_src,
-                     "note": "dominant kernel timed alone, one launch over %d crops; achieved = algorithmic bytes of that launch / CUDA-event time" % kern[dom]["crops_per_launch"],
-                     "step_share_ms": share,
-                     "step": {"alg_bytes_per_sample": step.bytes_per_sample(), "achieved": value / world / HANDS_PER_SAMPLE * step.bytes_per_sample() / 1e9,
-                              "frac": value / world / HANDS_PER_SAMPLE * step.bytes_per_sample() / 1e9 / peak},
-                     "kernels": kern, "families": fam},
+        "e2e_fp32_source": e2e_f32,
+        "roofline": {"bound": "hbm", "kernel": "fused C4 step (all kernels of one fwd+bwd pass)", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": step_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "achieved = algorithmic bytes of the whole step (SURVEY.md 8(d): %.0f B/sample) / device time of the timed region; "
+                             "per-kernel fractions (each kernel timed alone, one launch over %d crops) are under `kernels`, dram traffic per launch "
+                             "from %s" % (bps, kern[dom]["crops_per_launch"], traffic_src),
+                     "alg_bytes_per_sample": bps,
+                     "tensor_peak_tf32_tflops": tf32_peak, "tensor_peak_source": "measured here: torch.matmul fp32 with allow_tf32, 8192^3, best of 10",
+                     "tensor_frac": (mano_hps * L.F_GEMM / (tf32_peak * 1e12)) if tf32_peak else None,
+                     "tensor_note": "MANO head r+l alone (fwd+bwd families above): hands/s x %.0f algorithmic contraction FLOP/hand / measured TF32 peak; "
+                                    "MMA passes actually issued (3xTF32) are not credited" % L.F_GEMM,
+                     "dominant_kernel": dom, "step_share_ms": share, "overlap": overlap, "kernels": kern, "families": fam},
+        "configs": configs,
     }
     if world == 1 and not args.no_cpu_baseline:
-        hps, dt = time_cpu_reference(args.ref_samples, 2, 1)
-        line["cpu_baseline"] = {"value": hps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "cpu": cpu_model(),
-                                "sample": f"{args.ref_samples} samples ({args.ref_samples * HANDS_PER_SAMPLE} hands + crops) x 2 timed steps of the same workload; oracle = reference torch ops on CPU, all host threads"}
+        best, var = cpu_baseline_variants(args.ref_samples, 2, 1, want_pool=not args.quick)
+        line["cpu_baseline"] = {"value": var[best]["value"], "unit": UNIT, "cores": var[best]["cores"], "kind": "port", "cpu": cpu_model(), "variant": best,
+                                "variants": var,
+                                "sample": f"{args.ref_samples} samples ({args.ref_samples * HANDS_PER_SAMPLE} hands + crops) x 2 timed steps of the same workload; oracle = reference torch ops on CPU"}
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(step, args, dev, world, barrier):
+def L_c5(dev, world, rank, args):
+    """C5: HaMeR-light MANO head training step with the parameter-gradient all-reduce (scripts/c5_hamer_head.py), both the
+    read-out-sized (894 KB) and the decoder-head-sized (158 MB) gradient."""
+    from scripts import c5_hamer_head as C5
+
+    out = {}
+    for full in (False, True):
+        try:
+            out["full_head_158MB" if full else "readouts_894KB"] = C5.run(dev, world, rank, batch=8192, steps=10, warmup=3, full_head=full)
+        except Exception as exc:  # keep the headline line even if a side leg fails
+            out["error"] = str(exc)[:200]
+    return out
+
+
+def c4_true_shard(dev, world, rank, S, barrier, args):
+    """C4 at its stated shard size (65,536 samples / world per GPU), device-timed like the headline (max over ranks)."""
+    import torch.distributed as dist
+
+    from hands_b200.step import GeometryStep
+
+    st = GeometryStep(S, dev, img_res=IMG_RES, seed=1000 + rank)
+    for _ in range(2):
+        st.run()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 3
+    e0.record()
+    for _ in range(k):
+        st.run()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del st
+    torch.cuda.empty_cache()
+    el = float(t.item())
+    return {"samples_per_gpu": S, "global_samples": S * world, "ms_per_step": el / k * 1e3, "value": S * HANDS_PER_SAMPLE * world * k / el, "unit": UNIT}
+
+
+def run_e2e(step, args, dev, world, barrier, src_u8=True, steps=None):
     """Same workload with HOST buffers: per step, pinned H2D of the samples' inputs (source images, boxes,
     intrinsics, poses, shapes, cameras) and D2H of the per-hand gradients + one metric scalar, all inside the
     timed region.  The batch is processed in chunks of `--e2e-chunk` samples through two device buffer sets so the
@@ -339,7 +398,7 @@ def run_e2e(step, args, dev, world, barrier):
     nch = S // CH
     if nch * CH != S:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": "samples not divisible by e2e chunk"}
-    sets = [GeometryStep(CH, dev, img_res=IMG_RES, seed=100 + k) for k in range(2)]
+    sets = [GeometryStep(CH, dev, img_res=IMG_RES, seed=100 + k, src_u8=src_u8) for k in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
 
     def dev_inputs(gs):
@@ -358,7 +417,10 @@ def run_e2e(step, args, dev, world, barrier):
         # host side: the full batch in pinned memory (inputs) and pinned result buffers
         host_in = [torch.empty((nch,) + tuple(t.shape), dtype=t.dtype, pin_memory=True) for t in dev_inputs(sets[0])]
         for hb, t in zip(host_in, dev_inputs(step)):
-            hb.view((S * (t.shape[0] // S),) + tuple(t.shape[1:])).copy_(t)
+            if hb.dtype == t.dtype:
+                hb.view((S * (t.shape[0] // S),) + tuple(t.shape[1:])).copy_(t)
+            else:   # 8-bit source images: synthetic bytes (the main step holds the fp32 form)
+                hb.random_(0, 256)
         host_out = [torch.empty((nch,) + tuple(t.shape), dtype=t.dtype, pin_memory=True) for t in dev_outputs(sets[0])]
         metric_host = torch.empty(nch, dtype=torch.float32, pin_memory=True)
     except RuntimeError as exc:  # pinned allocation refused
@@ -386,7 +448,7 @@ def run_e2e(step, args, dev, world, barrier):
                 hb[c].copy_(o, non_blocking=True)
             metric_host[c : c + 1].copy_(gs.hands[0]["j2d"][0, 0, :1], non_blocking=True)
 
-    k = max(2, min(args.steps, 5))
+    k = steps or max(2, min(args.steps, 5))
     for _ in range(2):
         one()
     barrier()
@@ -405,6 +467,9 @@ def run_e2e(step, args, dev, world, barrier):
         el = float(t.item())
     return {"value": S * HANDS_PER_SAMPLE * world * k / el, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": k, "ms_per_step": el / k * 1e3, "wall_ms_per_step": wall / k * 1e3, "chunk_samples": CH,
+            "source_image_dtype": "uint8 (normalisation fused into the crop forward, hb_pcl_fwd_u8)" if src_u8 else "float32 (normalised on the host)",
+            "h2d_gbs": h2d * k / el / 1e9,
+            "d2h": "per-hand gradients (g_rotmat, g_betas, g_cam) + one metric scalar per chunk; crops and g_img stay on the device for the backbone",
             "pipeline": "H2D of chunk c+1 overlaps kernels of chunk c (2 device buffer sets)"}
 
 
@@ -415,11 +480,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=8192, help="samples per GPU per step (C4: 65536 / 8)")
-    ap.add_argument("--ref-samples", type=int, default=64, help="samples per CPU-reference step (bounded sample)")
+    ap.add_argument("--ref-samples", type=int, default=256, help="samples per CPU-reference step (bounded sample)")
     ap.add_argument("--e2e-chunk", type=int, default=1024, help="samples per pipelined e2e chunk")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the side legs (other configs, fp32-source e2e, CPU worker pool)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

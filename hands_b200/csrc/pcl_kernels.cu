@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
   __shared__ float lut[U8 ? C * 256 : 1];
   __shared__ float tu[RT ? RT : 1];        // linspace(0,1,s) of the crop's columns (compile-time resolution only)
   __shared__ float tv[RT ? PCL_TV : 1];    // ... and of the sub-block's intermediate rows
-  __shared__ float2 coltab[RT ? RT : 1];   // per output column: (weight of the upper tap, lower tap index) of the horizontal resize
+  __shared__ __align__(16) float2 coltab[RT ? RT : 1];   // per output column: (weight of the upper tap, lower tap index) of the horizontal resize
   const int q = blockIdx.y;
   const Crop c = load_crop(params + (size_t)q * PF);
   const int s = c.s;

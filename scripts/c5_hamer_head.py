@@ -57,6 +57,16 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    res = run(dev, world, rank, args.batch, args.steps, args.warmup, args.full_head)
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run(dev, world, rank, batch=8192, steps=20, warmup=3, full_head=False):
+    """One measurement (all ranks call it; the process group already exists when world > 1).  Returns the result dict."""
+    args = argparse.Namespace(batch=batch, steps=steps, warmup=warmup, full_head=full_head)
     torch.manual_seed(0)  # same initial parameters on every rank (what DDP's broadcast gives)
     B = args.batch
     heads = {True: MANOHead(True, 1000.0, 224, synthetic=True).to(dev), False: MANOHead(False, 1000.0, 224, synthetic=True).to(dev)}
@@ -119,13 +129,10 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        grad_bytes = 4 * sum(p.numel() for p in params)
-        print(json.dumps({"config": "C5 HaMeR-light MANO head + grad all-reduce", "n_gpus": world, "batch_per_gpu": B, "ms_per_step": float(ms),
-                          "hands_per_s": 2 * B * world / (float(ms) * 1e-3), "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-                          "loss": float(last["loss"])}))
-    if world > 1:
-        dist.destroy_process_group()
+    grad_bytes = 4 * sum(p.numel() for p in params)
+    return {"config": "C5 HaMeR-light MANO head + grad all-reduce", "n_gpus": world, "batch_per_gpu": B, "ms_per_step": float(ms),
+            "hands_per_s": 2 * B * world / (float(ms) * 1e-3), "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+            "loss": float(last["loss"])}
 
 
 if __name__ == "__main__":

@@ -81,20 +81,24 @@ def test_C2_head_fwd_bwd_B1024_against_oracle(heads, dev, is_rhand):
 def _oracle_pcl(img, bbox, K, res, cpi, w):
     nt = torch.get_num_threads()
     torch.set_num_threads(1)   # torch's bilinear kernels differ by 1 ulp between 1 and N threads; the goldens are 1-thread
+    crops, rots, grads = [], [], []
     try:
-        xr = img.clone().requires_grad_(True)
-        ref_crop, ref_rot = O.perspective_crop(xr.repeat_interleave(cpi, dim=0) if cpi > 1 else xr, bbox, K, res)
-        (ref_g,) = torch.autograd.grad((ref_crop * w).sum(), xr)
+        for b in range(img.shape[0]):   # one autograd leaf per source image (a slice of one big leaf costs a batch-sized zero gradient per crop)
+            xr = img[b : b + 1].clone().requires_grad_(True)
+            sl = slice(b * cpi, (b + 1) * cpi)
+            c, r = O.perspective_crop(xr.expand(cpi, -1, -1, -1), bbox[sl], K[sl], res)
+            (gx,) = torch.autograd.grad((c * w[sl]).sum(), xr)
+            crops.append(c.detach()); rots.append(r); grads.append(gx)
     finally:
         torch.set_num_threads(nt)
-    return ref_crop.detach(), ref_rot, ref_g
+    return torch.cat(crops), torch.cat(rots), torch.cat(grads)
 
 
 _C3 = {}
 
 
 def _c3_case():
-    """Inputs and oracle results of the C3 case, computed once (the single-threaded oracle takes ~70 s for 1024 crops)."""
+    """Inputs and oracle results of the C3 case, computed once (the single-threaded oracle takes a few seconds for 1024 crops)."""
     if not _C3:
         n, res = 1024, 224
         img, bbox, K = synthetic_pcl_inputs(n, seed=33, img_res=res, smin=res // 4, smax=3 * res // 4)
