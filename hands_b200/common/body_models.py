@@ -40,6 +40,30 @@ def seal_mano_mesh(v3d, faces, is_rhand):
     return torch.cat((v3d, centre), dim=1), torch.cat((faces, fan), dim=0)
 
 
+class MANODecimator:
+    """Drop-in for the reference's MANODecimator (common/body_models.py:11-32): the 195x778 ARCTIC mesh down-sampler.
+    `downsample(verts (B,778,3), is_right) -> (B,195,3)` = D @ verts.  A plain dense matrix product -- issued as ONE
+    library GEMM (cuBLAS through torch.matmul over the (778, 3B) view) instead of the reference's `D.repeat(B,1,1)` + bmm,
+    which materialises B copies of D (607 KB each).  Constants come from
+    `$DATA_DIR/arctic/data/arctic_data/data/meta/mano_decimator_195.npy` like the reference (read lazily, once, not on every
+    construction as src/models/generic/wrapper.py:81 does), or from `data={"D_right": ..., "D_left": ...}`."""
+
+    def __init__(self, data=None):
+        if data is None:
+            path = f"{os.environ['DATA_DIR']}/arctic/data/arctic_data/data/meta/mano_decimator_195.npy"
+            data = np.load(path, allow_pickle=True).item()
+        self.data = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in data.items() if "D" in k}
+
+    def downsample(self, verts, is_right):
+        flag = "right" if is_right else "left"
+        D = self.data[f"D_{flag}"]
+        if D.device != verts.device:
+            D = self.data[f"D_{flag}"] = D.to(verts.device)
+        B = verts.shape[0]
+        flat = verts.permute(1, 0, 2).reshape(verts.shape[1], B * 3)           # (778, 3B)
+        return torch.matmul(D, flat).reshape(D.shape[0], B, 3).permute(1, 0, 2).contiguous()
+
+
 def _to_np(x):
     """MANO pickles hold chumpy arrays / scipy sparse matrices; reduce to a dense float array."""
     if hasattr(x, "todense"):

@@ -216,9 +216,127 @@ __global__ void kpe_kernel(const int32_t* __restrict__ bbox, const float* __rest
   }
 }
 
+// ---- masked vector MSE terms: cam_t.wp (+ .init), relative translation l-r, pose and beta regressions ------------------
+// src/callbacks/loss/loss_arctic_sf.py:52-69,94-129,146-158 with src/utils/loss_modules.py:99-113 (vector_loss, MSE,
+// return_mean=False, dist * is_valid[..., None]; an all-invalid batch gives zeros -- the same numbers), gated per sample
+// by meta_info['is_*_loss'], reduced with .mean() over B*D elements.
+//   d[b][e] = (pred[b][e] - pred_minus[b][e]) - (gt[b][e] - gt_minus[b][e])          (the `_minus` operands are optional)
+//   sum     = sum_b valid[b] * valid2[b] * gate[b] * ( sum_e d^2  +  sum_e (pred2[b][e] - gt[b][e] + gt_minus)^2 if pred2 )
+// One warp per sample; partial[b] then the fixed-order single-block reduction: bit-reproducible.
+struct VecArgs {
+  const float* pred; const float* pred_minus; const float* gt; const float* gt_minus; const float* pred2;
+  const float* valid; const float* valid2; const float* gate; int B; int D;
+};
+
+__device__ __forceinline__ float vec_mask(const VecArgs& a, int b) {
+  float m = 1.0f;
+  if (a.valid) m *= __ldg(a.valid + b);
+  if (a.valid2) m *= __ldg(a.valid2 + b);
+  if (a.gate) m *= __ldg(a.gate + b);
+  return m;
+}
+
+__global__ void __launch_bounds__(128) vec_loss_fwd_kernel(VecArgs a, float* __restrict__ partial) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= a.B) return;
+  float acc = 0.f;
+  for (int e = lane; e < a.D; e += 32) {
+    const size_t o = (size_t)b * a.D + e;
+    const float t = __ldg(a.gt + o) - (a.gt_minus ? __ldg(a.gt_minus + o) : 0.f);
+    const float d = (__ldg(a.pred + o) - (a.pred_minus ? __ldg(a.pred_minus + o) : 0.f)) - t;
+    acc = fmaf(d, d, acc);
+    if (a.pred2) { const float d2 = __ldg(a.pred2 + o) - t; acc = fmaf(d2, d2, acc); }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) partial[b] = acc * vec_mask(a, b);
+}
+
+__global__ void __launch_bounds__(1024) vec_reduce_kernel(const float* __restrict__ partial, int B, float* __restrict__ sum) {
+  __shared__ float sh[1024];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += 1024) acc += partial[b];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int m = 512; m > 0; m >>= 1) {
+    if (threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sum[0] = sh[0];
+}
+
+__global__ void __launch_bounds__(128) vec_loss_bwd_kernel(VecArgs a, const float* __restrict__ g_loss, float* __restrict__ g_pred,
+                                                           float* __restrict__ g_pred_minus, float* __restrict__ g_pred2) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= a.B) return;
+  const float k = 2.0f * vec_mask(a, b) * __ldg(g_loss) / ((float)a.B * (float)a.D);   // loss = sum / (B*D)
+  for (int e = lane; e < a.D; e += 32) {
+    const size_t o = (size_t)b * a.D + e;
+    const float t = __ldg(a.gt + o) - (a.gt_minus ? __ldg(a.gt_minus + o) : 0.f);
+    const float d = (__ldg(a.pred + o) - (a.pred_minus ? __ldg(a.pred_minus + o) : 0.f)) - t;
+    if (g_pred) g_pred[o] = k * d;
+    if (g_pred_minus) g_pred_minus[o] = -k * d;
+    if (g_pred2) g_pred2[o] = a.pred2 ? k * (__ldg(a.pred2 + o) - t) : 0.f;
+  }
+}
+
+// pytorch3d axis_angle_to_matrix as the reference applies it to the GT pose (loss_arctic_sf.py:48-49) =
+// quaternion_to_matrix(axis_angle_to_quaternion(aa)) (common/rot.py:754-784, 86-115)
+__global__ void aa_to_matrix_kernel(const float* __restrict__ aa, int N, float* __restrict__ R) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float x = aa[(size_t)n * 3], y = aa[(size_t)n * 3 + 1], z = aa[(size_t)n * 3 + 2];
+  const float ang = sqrtf(x * x + y * y + z * z);
+  const float half = ang * 0.5f;
+  const float eps = 1e-6f;
+  const float soa = fabsf(ang) < eps ? 0.5f - (ang * ang) / 48.0f : sinf(half) / ang;
+  const float r = cosf(half), i = x * soa, j = y * soa, k = z * soa;
+  const float two_s = 2.0f / (r * r + i * i + j * j + k * k);
+  float* o = R + (size_t)n * 9;
+  o[0] = 1.f - two_s * (j * j + k * k); o[1] = two_s * (i * j - k * r);       o[2] = two_s * (i * k + j * r);
+  o[3] = two_s * (i * j + k * r);       o[4] = 1.f - two_s * (i * i + k * k); o[5] = two_s * (j * k - i * r);
+  o[6] = two_s * (i * k - j * r);       o[7] = two_s * (j * k + i * r);       o[8] = 1.f - two_s * (i * i + j * j);
+}
+
 }  // namespace hb
 
 using namespace hb;
+
+extern "C" int hb_vec_loss_fwd(const float* pred, const float* pred_minus, const float* gt, const float* gt_minus, const float* pred2,
+                               const float* valid, const float* valid2, const float* gate, int B, int D, float* partial, float* sum, void* stream) {
+  if (B < 0 || D <= 0 || !sum || (B > 0 && (!pred || !gt || !partial))) { set_error("hb_vec_loss_fwd: bad argument"); return HB_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  VecArgs a{pred, pred_minus, gt, gt_minus, pred2, valid, valid2, gate, B, D};
+  if (B > 0) {
+    vec_loss_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(a, partial);
+    g_launches++;
+    int rc = check_launch("vec_loss_fwd_kernel");
+    if (rc) return rc;
+  }
+  vec_reduce_kernel<<<1, 1024, 0, st>>>(partial, B, sum);
+  g_launches++;
+  return check_launch("vec_reduce_kernel");
+}
+
+extern "C" int hb_vec_loss_bwd(const float* pred, const float* pred_minus, const float* gt, const float* gt_minus, const float* pred2,
+                               const float* valid, const float* valid2, const float* gate, int B, int D, const float* g_loss,
+                               float* g_pred, float* g_pred_minus, float* g_pred2, void* stream) {
+  if (B < 0 || D <= 0 || (B > 0 && (!pred || !gt || !g_loss))) { set_error("hb_vec_loss_bwd: bad argument"); return HB_E_ARG; }
+  if (B == 0) return 0;
+  VecArgs a{pred, pred_minus, gt, gt_minus, pred2, valid, valid2, gate, B, D};
+  vec_loss_bwd_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a, g_loss, g_pred, g_pred_minus, g_pred2);
+  g_launches++;
+  return check_launch("vec_loss_bwd_kernel");
+}
+
+extern "C" int hb_axis_angle_to_matrix(const float* aa, int N, float* R, void* stream) {
+  if (N < 0 || (N > 0 && (!aa || !R))) { set_error("hb_axis_angle_to_matrix: bad argument"); return HB_E_ARG; }
+  if (N == 0) return 0;
+  aa_to_matrix_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(aa, N, R);
+  g_launches++;
+  return check_launch("aa_to_matrix_kernel");
+}
+
+
 
 static int kp_check(const char* what, const float* j3d, const float* j2d, const float* gt3, const float* gt2, const float* jv, int B) {
   if (B < 0 || (B > 0 && (!j3d || !j2d || !gt3 || !gt2 || !jv))) { set_error("%s: bad argument", what); return HB_E_ARG; }

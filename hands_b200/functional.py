@@ -77,7 +77,7 @@ class ManoHeadFunction(torch.autograd.Function):
     Reference: src/nets/hand_heads/mano_head.py:21-65 and smplx.MANO.forward."""
 
     @staticmethod
-    def forward(ctx, handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s, rot6d_layout=None):
+    def forward(ctx, handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s, rot6d_layout=None, materialise=None):
         lib = _lib.load()
         B = betas.shape[0]
         if rot6d_layout is not None:   # (B,16,6) 6D rotations, conversion fused in front of the log map
@@ -96,11 +96,15 @@ class ManoHeadFunction(torch.autograd.Function):
             raise RuntimeError(f"inputs on {dev} but MANO constants on {handle.device}")
         has_cam = cam is not None
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        vertices, joints3d = new(B, NV, 3), new(B, NOJ, 3)
-        v3d = new(B, NV, 3) if has_cam else None
-        j3d = new(B, NOJ, 3) if has_cam else None
-        j2d = new(B, NOJ, 2) if has_cam else None
-        cam_t = new(B, 3) if has_cam else None
+        # `materialise`: names of the outputs to write (None = all).  The C ABI skips NULL outputs, so a consumer that only
+        # reads j3d.cam / j2d.norm (the key-point losses) never pays the 18.7 KB/hand of vertex stores.
+        want = lambda k: materialise is None or k in materialise  # noqa: E731
+        vertices = new(B, NV, 3) if want("vertices") else None
+        joints3d = new(B, NOJ, 3) if want("joints3d") else None
+        v3d = new(B, NV, 3) if has_cam and want("v3d.cam") else None
+        j3d = new(B, NOJ, 3) if has_cam and want("j3d.cam") else None
+        j2d = new(B, NOJ, 2) if has_cam and want("j2d.norm") else None
+        cam_t = new(B, 3) if has_cam and want("cam_t") else None
         nbytes = lib.hb_mano_workspace_bytes(B, 0)
         ws = _workspace(nbytes, dev)
         with torch.cuda.device(dev):
@@ -133,8 +137,8 @@ class ManoHeadFunction(torch.autograd.Function):
                                       _ptr(g_j2d), _ptr(g_cam_t), _ptr(g_pose), _ptr(g_betas), _ptr(g_cam), _ptr(g_transl), _ptr(g_pre),
                                       _ptr(ws), nbytes, _stream())
         _lib.check(rc, "hb_mano_head_bwd")
-        # inputs: handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s, rot6d_layout
-        return None, g_pose, g_betas, g_cam, None, g_transl, g_pre, None, None, None
+        # inputs: handle, pose, betas, cam, K, transl, pre_rot, img_res, min_s, rot6d_layout, materialise
+        return None, g_pose, g_betas, g_cam, None, g_transl, g_pre, None, None, None, None
 
 
 class Rot6dToRotmatFunction(torch.autograd.Function):

@@ -75,3 +75,87 @@ def mrrpe_sums(j3d_cam_r, j3d_cam_l, gt_j3d_cam_r, gt_j3d_cam_l, valid=None):
         rc = lib.hb_mrrpe(*[_ptr(t) for t in args], _ptr(valid), B, _ptr(partial), _ptr(sums), _stream())
     _lib.check(rc, "hb_mrrpe")
     return sums
+
+
+class VectorLossFunction(torch.autograd.Function):
+    """loss = mean_b,e [ valid*valid2*gate * ( ((pred - pred_minus) - (gt - gt_minus))^2 + (pred2 - (gt - gt_minus))^2 ) ].
+    Gradients flow to pred, pred_minus and pred2; targets and masks are data.  (hb_vec_loss_fwd/bwd)"""
+
+    @staticmethod
+    def forward(ctx, pred, pred_minus, pred2, gt, gt_minus, valid, valid2, gate):
+        lib = _lib.load()
+        B = pred.shape[0]
+        D = pred[0].numel() if B else int(torch.tensor(pred.shape[1:]).prod())
+        f = lambda t, n: None if t is None else _f32c(t.reshape(B, D), n, (B, D))  # noqa: E731
+        pred, pred_minus, pred2, gt, gt_minus = f(pred, "pred"), f(pred_minus, "pred_minus"), f(pred2, "pred2"), f(gt, "gt"), f(gt_minus, "gt_minus")
+        valid, valid2, gate = _f32c(valid, "valid", (B,)), _f32c(valid2, "valid2", (B,)), _f32c(gate, "gate", (B,))
+        dev = pred.device
+        partial = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.hb_vec_loss_fwd(_ptr(pred), _ptr(pred_minus), _ptr(gt), _ptr(gt_minus), _ptr(pred2), _ptr(valid), _ptr(valid2), _ptr(gate), B, D,
+                                     _ptr(partial), _ptr(out), _stream())
+        _lib.check(rc, "hb_vec_loss_fwd")
+        ctx.save_for_backward(pred, pred_minus, pred2, gt, gt_minus, valid, valid2, gate)
+        ctx.dims = (B, D)
+        return out[0] / float(max(B, 1) * D)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        pred, pred_minus, pred2, gt, gt_minus, valid, valid2, gate = ctx.saved_tensors
+        B, D = ctx.dims
+        g = g.reshape(1).contiguous().float()
+        need = ctx.needs_input_grad
+        g_pred = torch.empty_like(pred) if need[0] else None
+        g_minus = torch.empty_like(pred_minus) if (pred_minus is not None and need[1]) else None
+        g_pred2 = torch.empty_like(pred2) if (pred2 is not None and need[2]) else None
+        with torch.cuda.device(pred.device):
+            rc = lib.hb_vec_loss_bwd(_ptr(pred), _ptr(pred_minus), _ptr(gt), _ptr(gt_minus), _ptr(pred2), _ptr(valid), _ptr(valid2), _ptr(gate), B, D,
+                                     _ptr(g), _ptr(g_pred), _ptr(g_minus), _ptr(g_pred2), _stream())
+        _lib.check(rc, "hb_vec_loss_bwd")
+        return g_pred, g_minus, g_pred2, None, None, None, None, None
+
+
+def vector_loss(pred, gt, valid=None, gate=None, pred2=None, pred_minus=None, gt_minus=None, valid2=None):
+    """One masked, gated vector MSE term of `compute_loss_light` (src/callbacks/loss/loss_arctic_sf.py:52-69, 94-158 with
+    src/utils/loss_modules.py:99-113): returns the scalar the reference calls `loss_*.mean()`.  Shapes (B, ...) with equal
+    trailing sizes; `pred2` is a second prediction scored against the same target (cam_t.wp.init); `pred_minus`/`gt_minus`
+    are subtracted first (the relative translation l - r); valid/valid2/gate are (B,) masks."""
+    shape = pred.shape
+    v = lambda t: None if t is None else t.reshape(shape)  # noqa: E731
+    return VectorLossFunction.apply(pred, v(pred_minus), v(pred2), gt.reshape(shape), v(gt_minus), valid, valid2, gate)
+
+
+def axis_angle_to_matrix(aa):
+    """pytorch3d.transforms.axis_angle_to_matrix as the reference applies it to the GT pose (loss_arctic_sf.py:48-49):
+    (...,3) -> (...,3,3); no gradient (GT side)."""
+    lead = aa.shape[:-1]
+    x = _f32c(aa.detach().reshape(-1, 3), "axis_angle", (None, 3))
+    R = torch.empty(x.shape[0], 3, 3, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hb_axis_angle_to_matrix(_ptr(x), x.shape[0], _ptr(R), _stream()), "hb_axis_angle_to_matrix")
+    return R.reshape(lead + (3, 3))
+
+
+def compute_loss_light(pred, gt, meta_info, img_res=224):
+    """Drop-in for the MANO terms of the reference's `compute_loss_light` (src/callbacks/loss/loss_arctic_sf.py:20-158): same
+    dictionary of (loss, weight) pairs under the same keys, every term one fused launch (+ one fixed-order reduction) on the
+    path's outputs.  `pred` / `gt` / `meta_info` use the reference's key names; masks are float tensors like the reference's.
+    (The optional grasp term, :160-171, is a cross-entropy on a classifier head -- not on the geometry path.)"""
+    out = {}
+    rv, lv = gt["right_valid"], gt["left_valid"]
+    gates = {k: meta_info[k].float() for k in ("is_cam_loss", "is_j2d_loss", "is_j3d_loss", "is_pose_loss", "is_beta_loss")}
+    for side, valid, jv in (("r", rv, gt["joints_valid_r"]), ("l", lv, gt["joints_valid_l"])):
+        gt_pose = axis_angle_to_matrix(gt[f"mano.pose.{side}"].reshape(-1, 3)).reshape(-1, 16, 3, 3)
+        out[f"loss/mano/cam_t/{side}"] = (vector_loss(pred[f"mano.cam_t.wp.{side}"], gt[f"mano.cam_t.wp.{side}"], valid, gates["is_cam_loss"],
+                                                      pred2=pred[f"mano.cam_t.wp.init.{side}"]).view(-1), 1.0)
+        l3, l2, _ = keypoint_losses(pred[f"mano.j3d.cam.{side}"], pred[f"mano.j2d.norm.{side}"], gt[f"mano.j3d.cam.{side}"], gt[f"mano.j2d.norm.{side}"],
+                                    jv, None, gates["is_j3d_loss"], gates["is_j2d_loss"], img_res)
+        out[f"loss/mano/kp2d/{side}"] = (l2.view(-1), 5.0)
+        out[f"loss/mano/kp3d/{side}"] = (l3.view(-1), 5.0)
+        out[f"loss/mano/pose/{side}"] = (vector_loss(pred[f"mano.pose.{side}"], gt_pose, valid, gates["is_pose_loss"]).view(-1), 10.0)
+        out[f"loss/mano/beta/{side}"] = (vector_loss(pred[f"mano.beta.{side}"], gt[f"mano.beta.{side}"], valid, gates["is_beta_loss"]).view(-1), 0.001)
+    out["loss/mano/transl/l"] = (vector_loss(pred["mano.cam_t.wp.l"], gt["mano.cam_t.wp.l"], rv, gates["is_cam_loss"], pred_minus=pred["mano.cam_t.wp.r"],
+                                             gt_minus=gt["mano.cam_t.wp.r"], valid2=lv).view(-1), 1.0)
+    return out

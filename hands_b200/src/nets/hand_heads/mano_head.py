@@ -12,8 +12,16 @@ from ....functional import ManoHeadFunction
 
 
 class MANOHead(nn.Module):
-    def __init__(self, is_rhand, focal_length, img_res, synthetic=False):
+    OUTPUTS = ("vertices", "joints3d", "v3d.cam", "j3d.cam", "j2d.norm", "cam_t")
+
+    def __init__(self, is_rhand, focal_length, img_res, synthetic=False, materialise=None):
+        """materialise (extension, default None = all six): the subset of OUTPUTS to compute into memory; the other keys are
+        absent from the result (reading one raises KeyError).  E.g. ("j3d.cam", "j2d.norm") for a step whose loss reads only
+        the key-points (loss_arctic_sf.py:70-92): the 778-vertex tensors are then never written."""
         super().__init__()
+        if materialise is not None and not set(materialise) <= set(self.OUTPUTS):
+            raise ValueError(f"materialise: unknown output(s) {sorted(set(materialise) - set(self.OUTPUTS))}")
+        self.materialise = None if materialise is None else frozenset(materialise)
         self.mano = build_mano_aa(is_rhand, synthetic=synthetic)
         self.focal_length = focal_length
         self.img_res = img_res
@@ -37,18 +45,18 @@ class MANOHead(nn.Module):
             rotmat_original = rotmat.clone()
         handle = self.mano.handle(shape.device)
         vertices, v3d_cam, joints3d, j3d_cam, j2d_norm, cam_t = ManoHeadFunction.apply(
-            handle, pose, shape, cam, K, None, pre_rot, float(self.img_res), 0.1
+            handle, pose, shape, cam, K, None, pre_rot, float(self.img_res), 0.1, None, self.materialise
         )
+        return self._pack(cam, cam_t, joints3d, vertices, j3d_cam, v3d_cam, j2d_norm, shape, rotmat_original)
+
+    def _pack(self, cam, cam_t, joints3d, vertices, j3d_cam, v3d_cam, j2d_norm, shape, pose):
         output = xdict()
         output["cam_t.wp"] = cam
-        output["cam_t"] = cam_t
-        output["joints3d"] = joints3d
-        output["vertices"] = vertices
-        output["j3d.cam"] = j3d_cam
-        output["v3d.cam"] = v3d_cam
-        output["j2d.norm"] = j2d_norm
+        for key, val in (("cam_t", cam_t), ("joints3d", joints3d), ("vertices", vertices), ("j3d.cam", j3d_cam), ("v3d.cam", v3d_cam), ("j2d.norm", j2d_norm)):
+            if val is not None:
+                output[key] = val
         output["beta"] = shape
-        output["pose"] = rotmat_original
+        output["pose"] = pose
         return output.postfix(".r" if self.is_rhand else ".l")
 
     def forward_rot6d(self, pose6d, shape, cam, K, layout="rows", pre_rot=None):
@@ -62,21 +70,11 @@ class MANOHead(nn.Module):
         x6 = pose6d.reshape(B, 16, 6)
         handle = self.mano.handle(shape.device)
         vertices, v3d_cam, joints3d, j3d_cam, j2d_norm, cam_t = ManoHeadFunction.apply(
-            handle, x6, shape, cam, K, None, pre_rot, float(self.img_res), 0.1, layout
+            handle, x6, shape, cam, K, None, pre_rot, float(self.img_res), 0.1, layout, self.materialise
         )
-        output = xdict()
-        output["cam_t.wp"] = cam
-        output["cam_t"] = cam_t
-        output["joints3d"] = joints3d
-        output["vertices"] = vertices
-        output["j3d.cam"] = j3d_cam
-        output["v3d.cam"] = v3d_cam
-        output["j2d.norm"] = j2d_norm
-        output["beta"] = shape
         pose_mats = Rot6dToRotmatFunction.apply(x6.reshape(-1, 6), layout).reshape(B, 16, 3, 3)
         if pre_rot is not None:   # as in forward(): the returned pose carries the rotated global orientation
             from ....pcl import apply_virtual_rotation
 
             pose_mats = apply_virtual_rotation(pre_rot, pose_mats)
-        output["pose"] = pose_mats
-        return output.postfix(".r" if self.is_rhand else ".l")
+        return self._pack(cam, cam_t, joints3d, vertices, j3d_cam, v3d_cam, j2d_norm, shape, pose_mats)

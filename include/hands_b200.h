@@ -152,6 +152,25 @@ int hb_kp_loss_fwd(const float* j3d_cam, const float* j2d_norm, const float* gt_
 int hb_kp_loss_bwd(const float* j3d_cam, const float* j2d_norm, const float* gt_j3d_cam, const float* gt_j2d_norm,
                    const float* joints_valid, const float* gate_j3d, const float* gate_j2d, int B, const float* g_loss_kp3d,
                    const float* g_loss_kp2d, float* g_j3d_cam, float* g_j2d_norm, void* stream);
+/* Masked vector MSE terms of compute_loss_light (src/callbacks/loss/loss_arctic_sf.py:52-69 pose/beta via mano_loss, :94-129
+ * cam_t.wp (+ cam_t.wp.init) and the relative translation l - r, gated at :134-145, .mean() at :146-158; vector_loss =
+ * src/utils/loss_modules.py:99-113 with MSE, return_mean=False):
+ *   d[b][e] = (pred - pred_minus)[b][e] - (gt - gt_minus)[b][e]                       (pred_minus, gt_minus or NULL)
+ *   *sum    = sum_b valid[b] * valid2[b] * gate[b] * ( sum_e d^2 + sum_e (pred2 - (gt - gt_minus))^2 )   (pred2 or NULL)
+ *   loss    = *sum / (B * D)
+ * All arrays (B, D) fp32 on the device; valid, valid2, gate (B) or NULL (= 1).  partial: B floats of scratch.  Fixed
+ * reduction order (bit-reproducible).  Uses: cam_t.wp.{r,l} with pred2 = cam_t.wp.init (D = 3); transl/l with
+ * pred = cam_t.wp.l, pred_minus = cam_t.wp.r, valid2 = left_valid (D = 3); pose (D = 144) and beta (D = 10). */
+int hb_vec_loss_fwd(const float* pred, const float* pred_minus, const float* gt, const float* gt_minus, const float* pred2,
+                    const float* valid, const float* valid2, const float* gate, int B, int D, float* partial, float* sum,
+                    void* stream);
+/* Gradients of loss = *sum / (B*D), scaled by the device scalar g_loss, w.r.t. pred, pred_minus, pred2 (each or NULL). */
+int hb_vec_loss_bwd(const float* pred, const float* pred_minus, const float* gt, const float* gt_minus, const float* pred2,
+                    const float* valid, const float* valid2, const float* gate, int B, int D, const float* g_loss,
+                    float* g_pred, float* g_pred_minus, float* g_pred2, void* stream);
+/* pytorch3d axis_angle_to_matrix as applied to the GT pose at loss_arctic_sf.py:48-49 (= common/rot.py:754-784 then :86-115):
+ * aa (N,3) -> R (N,3,3).  GT side, no gradient. */
+int hb_axis_angle_to_matrix(const float* aa, int N, float* R, void* stream);
 /* MRRPE partial sums: sums[0] = sum over valid samples of ||(root_l - root_r)_pred - (root_l - root_r)_gt||, sums[1] = count;
  * roots are joint 0 of the (B,21,3) arrays; valid (B) or NULL. */
 int hb_mrrpe(const float* j3d_cam_r, const float* j3d_cam_l, const float* gt_j3d_cam_r, const float* gt_j3d_cam_l,

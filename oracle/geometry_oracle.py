@@ -280,6 +280,38 @@ def keypoint_metric_sums(j3d, j2d, gt3, gt2, joints_valid, hand_valid, img_res):
     return (dist3 * hand_valid).sum(), hand_valid.sum(), (dist2 * v2).sum(), v2.sum()
 
 
+def vector_loss_term(pred, gt, valid=None, gate=None, pred2=None):
+    """One masked vector MSE term of compute_loss_light: src/utils/loss_modules.py:99-113 (vector_loss, MSE, return_mean=False:
+    dist.reshape(B,-1) * is_valid[...,None]; zeros when is_valid.sum()==0, which is the same number), the optional second
+    prediction against the same target (`cam_t.wp.init`, loss_arctic_sf.py:116-129), the per-sample gate of :134-145 and the
+    .mean() of :146-158."""
+    B = pred.shape[0]
+    d = ((pred - gt) ** 2).reshape(B, -1)
+    if pred2 is not None:
+        d = d + ((pred2 - gt) ** 2).reshape(B, -1)
+    if valid is not None:
+        d = d * valid[..., None]
+    if gate is not None:
+        d = d * gate[..., None]
+    return d.mean()
+
+
+def axis_angle_to_matrix(aa):
+    """pytorch3d axis_angle_to_matrix (loss_arctic_sf.py:48-49) = common/rot.py:754-784 (axis_angle_to_quaternion) then
+    :86-115 (quaternion_to_matrix)."""
+    ang = torch.norm(aa, p=2, dim=-1, keepdim=True)
+    half = ang * 0.5
+    small = ang.abs() < 1e-6
+    soa = torch.where(small, 0.5 - ang * ang / 48, torch.sin(half) / torch.where(small, torch.ones_like(ang), ang))
+    q = torch.cat([torch.cos(half), aa * soa], dim=-1)
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack([1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)], -1)
+    return o.reshape(aa.shape[:-1] + (3, 3))
+
+
 def mrrpe_sums(root_r, root_l, gt_root_r, gt_root_l, valid):
     """common/metrics.py:47-55."""
     d = (((root_l - root_r) - (gt_root_l - gt_root_r)) ** 2).sum(dim=1).sqrt()

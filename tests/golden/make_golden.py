@@ -385,6 +385,106 @@ def golden_mano_head_reference_source():
     np.savez_compressed(os.path.join(HERE, "mano_head_ref.npz"), **{k: (v.astype(np.float32) if v.dtype == np.float64 else v) for k, v in out.items()})
 
 
+def golden_loss_light():
+    """The reference's own `compute_loss_light` (src/callbacks/loss/loss_arctic_sf.py:20-171).  The module imports pytorch3d
+    (absent) for one function, `axis_angle_to_matrix`; the function definition is exec'd from the file's AST with that name
+    bound to the reference's own port of it (common/rot.py: quaternion_to_matrix(axis_angle_to_quaternion(.)), the same
+    pytorch3d code) and every other name bound to src/utils/loss_modules.py -- nothing is copied."""
+    import ast
+
+    import src.utils.loss_modules as ref_lm
+
+    with open(os.path.join(REF, "src", "callbacks", "loss", "loss_arctic_sf.py")) as fh:
+        tree = ast.parse(fh.read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "compute_loss_light"]
+    assert len(fn) == 1
+    ns = {"torch": torch, "nn": torch.nn, "l1_loss": torch.nn.L1Loss(reduction="none"), "mse_loss": torch.nn.MSELoss(reduction="none"),
+          "axis_angle_to_matrix": lambda aa: ref_rot.quaternion_to_matrix(ref_rot.axis_angle_to_quaternion(aa))}
+    for name in ("compute_contact_devi_loss", "hand_kp3d_loss", "joints_loss", "mano_loss", "object_kp3d_loss", "vector_loss", "grasp_loss"):
+        ns[name] = getattr(ref_lm, name)
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "ref_compute_loss_light", "exec"), ns)
+    g = torch.Generator().manual_seed(31)
+    B = 24
+    rn = lambda *sh: torch.randn(*sh, generator=g)  # noqa: E731
+    mask = lambda p: (torch.rand(B, generator=g) > p).float()  # noqa: E731
+    pred, gt = {}, {}
+    for sd in ("r", "l"):
+        pred[f"mano.beta.{sd}"] = rn(B, 10)
+        pred[f"mano.pose.{sd}"] = random_rotmats(B * 16, g).reshape(B, 16, 3, 3)
+        pred[f"mano.j3d.cam.{sd}"] = 0.1 * rn(B, 21, 3) + torch.tensor([0.0, 0.0, 0.6])
+        pred[f"mano.j2d.norm.{sd}"] = 0.5 * rn(B, 21, 2)
+        pred[f"mano.cam_t.wp.{sd}"] = rn(B, 3)
+        pred[f"mano.cam_t.wp.init.{sd}"] = rn(B, 3)
+        gt[f"mano.pose.{sd}"] = 0.4 * rn(B, 48)
+        gt[f"mano.pose.{sd}"][0, :3] = 0.0          # small-angle branch of axis_angle_to_quaternion
+        gt[f"mano.beta.{sd}"] = rn(B, 10)
+        gt[f"mano.j3d.cam.{sd}"] = 0.1 * rn(B, 21, 3) + torch.tensor([0.0, 0.0, 0.6])
+        gt[f"mano.j2d.norm.{sd}"] = 0.5 * rn(B, 21, 2)
+        gt[f"mano.cam_t.wp.{sd}"] = rn(B, 3)
+        gt[f"joints_valid_{sd}"] = (torch.rand(B, 21, generator=g) > 0.2).float()
+    gt["is_valid"], gt["right_valid"], gt["left_valid"] = mask(0.1), mask(0.2), mask(0.2)
+    meta = {k: mask(0.3) for k in ("is_cam_loss", "is_j2d_loss", "is_j3d_loss", "is_pose_loss", "is_beta_loss")}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in pred.items()}
+    class Args(dict):     # easydict stand-in: .get() and attribute access (args.regress_center_corner, :196)
+        __getattr__ = dict.get
+
+    out = ns["compute_loss_light"](leaves, gt, meta, Args(regress_center_corner=False))
+    total = sum(l * w for l, w in out.values())
+    grads = torch.autograd.grad(total, list(leaves.values()), allow_unused=True)
+    sav = {"B": np.array(B)}
+    for k, v in pred.items():
+        sav["pred:" + k] = v.numpy()
+    for k, v in gt.items():
+        sav["gt:" + k] = v.numpy()
+    for k, v in meta.items():
+        sav["meta:" + k] = v.numpy()
+    for k, (l, w) in out.items():
+        sav["loss:" + k] = l.detach().numpy()
+        sav["weight:" + k] = np.array(w)
+    for k, gr in zip(leaves, grads):
+        sav["grad:" + k] = (gr if gr is not None else torch.zeros_like(pred[k])).numpy()
+    sav["gt_rotmat_r"] = ns["axis_angle_to_matrix"](gt["mano.pose.r"].reshape(-1, 3)).numpy()
+    np.savez_compressed(os.path.join(HERE, "loss_light.npz"), **sav)
+
+
+def golden_decimator():
+    """`MANODecimator.downsample` of the reference (common/body_models.py:11-32), class definition exec'd from the file's AST,
+    fed a synthetic 195x778 decimation matrix through a temporary $DATA_DIR (the real .npy is ARCTIC data, unavailable)."""
+    import ast
+    import tempfile
+
+    with open(os.path.join(REF, "common", "body_models.py")) as fh:
+        tree = ast.parse(fh.read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MANODecimator"]
+    assert len(cls) == 1
+    ns = {"np": np, "torch": torch, "os": os}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), "ref_mano_decimator", "exec"), ns)
+    g = torch.Generator().manual_seed(51)
+    D = {}
+    for flag in ("right", "left"):
+        d = torch.zeros(195, 778)
+        idx = torch.randint(0, 778, (195, 3), generator=g)
+        wts = torch.rand(195, 3, generator=g)
+        d.scatter_(1, idx, wts / wts.sum(1, keepdim=True))      # decimation rows: a few positive weights summing to one
+        D[f"D_{flag}"] = d.numpy()
+    verts = 0.05 * torch.randn(5, 778, 3, generator=g)
+    old = os.environ.get("DATA_DIR")
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "arctic", "data", "arctic_data", "data", "meta")
+        os.makedirs(path)
+        np.save(os.path.join(path, "mano_decimator_195.npy"), D, allow_pickle=True)
+        os.environ["DATA_DIR"] = tmp
+        try:
+            dec = ns["MANODecimator"]()
+            out_r, out_l = dec.downsample(verts, True), dec.downsample(verts, False)
+        finally:
+            if old is None:
+                del os.environ["DATA_DIR"]
+            else:
+                os.environ["DATA_DIR"] = old
+    np.savez_compressed(os.path.join(HERE, "decimator.npz"), D_right=D["D_right"], D_left=D["D_left"], verts=verts.numpy(), sub_r=out_r.numpy(), sub_l=out_l.numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     golden_logmap()
@@ -396,6 +496,8 @@ if __name__ == "__main__":
     golden_kpe()
     golden_mesh_constants()
     golden_mano_head_reference_source()
+    golden_loss_light()
+    golden_decimator()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -205,3 +205,38 @@ def test_mano_layer_state_dict_is_smplx_shaped():
         m2.load_state_dict(sd, strict=True)
     m._handles[("cuda", 0)] = ("stamp", object())     # stand-in for a live device handle
     assert pickle.loads(pickle.dumps(m))._handles == {} and copy.deepcopy(m)._handles == {}
+
+
+def test_loss_light_terms_match_reference(golden_dir):
+    """f2: the oracle's masked vector-MSE term and axis_angle_to_matrix against the reference's OWN compute_loss_light
+    (loss_arctic_sf.py:20-158, exec'd from the file by make_golden.py) on every cam_t / transl / pose / beta key."""
+    g = _load(golden_dir, "loss_light.npz")
+    P = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("pred:")}
+    G = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("gt:")}
+    M = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("meta:")}
+    close = lambda a, key: abs(float(a) - float(g["loss:" + key])) <= 2e-6 * max(1.0, abs(float(g["loss:" + key])))  # noqa: E731
+    assert float((O.axis_angle_to_matrix(G["mano.pose.r"].reshape(-1, 3)) - torch.from_numpy(g["gt_rotmat_r"])).abs().max()) <= 2e-7
+    for sd, valid in (("r", G["right_valid"]), ("l", G["left_valid"])):
+        assert close(O.vector_loss_term(P[f"mano.cam_t.wp.{sd}"], G[f"mano.cam_t.wp.{sd}"], valid, M["is_cam_loss"], pred2=P[f"mano.cam_t.wp.init.{sd}"]), f"loss/mano/cam_t/{sd}")
+        gt_pose = O.axis_angle_to_matrix(G[f"mano.pose.{sd}"].reshape(-1, 3)).reshape(-1, 16, 3, 3)
+        assert close(O.vector_loss_term(P[f"mano.pose.{sd}"], gt_pose, valid, M["is_pose_loss"]), f"loss/mano/pose/{sd}")
+        assert close(O.vector_loss_term(P[f"mano.beta.{sd}"], G[f"mano.beta.{sd}"], valid, M["is_beta_loss"]), f"loss/mano/beta/{sd}")
+        l3, l2 = O.keypoint_losses(P[f"mano.j3d.cam.{sd}"], P[f"mano.j2d.norm.{sd}"], G[f"mano.j3d.cam.{sd}"], G[f"mano.j2d.norm.{sd}"], G[f"joints_valid_{sd}"],
+                                   M["is_j3d_loss"], M["is_j2d_loss"])
+        assert close(l3, f"loss/mano/kp3d/{sd}") and close(l2, f"loss/mano/kp2d/{sd}")
+    assert close(O.vector_loss_term(P["mano.cam_t.wp.l"] - P["mano.cam_t.wp.r"], G["mano.cam_t.wp.l"] - G["mano.cam_t.wp.r"], G["right_valid"] * G["left_valid"], M["is_cam_loss"]),
+                 "loss/mano/transl/l")
+
+
+def test_mano_decimator_matches_reference(golden_dir):
+    """f4: the drop-in MANODecimator (one GEMM over the (778, 3B) view) against the reference's own class
+    (common/body_models.py:11-32, exec'd by make_golden.py with a synthetic decimation matrix)."""
+    from hands_b200.common.body_models import MANODecimator
+
+    g = _load(golden_dir, "decimator.npz")
+    dec = MANODecimator(data={"D_right": g["D_right"], "D_left": g["D_left"], "other": np.zeros(3)})
+    verts = torch.from_numpy(g["verts"])
+    for name, flag in (("r", True), ("l", False)):
+        out = dec.downsample(verts, flag)
+        assert out.shape == (5, 195, 3) and out.is_contiguous()
+        assert float((out - torch.from_numpy(g[f"sub_{name}"])).abs().max()) <= 1e-7
