@@ -416,23 +416,30 @@ __device__ __forceinline__ void gather_global(const SrcT* __restrict__ src, cons
 
 constexpr int PCL_TV = 40;   // rows of the per-sub-block linspace table (an intermediate band never has more: 16 * scale + 3, scale <= 1)
 
+constexpr int PCL_XB = 112;   // output columns per CTA of the fast forward (two column blocks at R = 224)
+
 template <int C, int RT, typename SrcT, bool V2>   // V2: out is 8-byte aligned and R even -> 64-bit stores
 __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT* __restrict__ img, const float* __restrict__ params, int crops_per_img, int R_arg,
-                                                                      float* __restrict__ out, int smem_bytes, int tma_ok, PclNorm nrm) {
+                                                                      float* __restrict__ out, int smem_bytes, int tma_ok, int nxb, PclNorm nrm) {
   const int R = RT ? RT : R_arg;
   constexpr bool U8 = sizeof(SrcT) == 1;
-  extern __shared__ __align__(16) float4 mid4[];  // [nrows][s] pixels, channels in .x .y .z .w; then the staged source tile (fp32)
+  extern __shared__ __align__(16) float4 mid4[];  // [nrows][ncol] pixels, channels in .x .y .z .w; then the staged source tile (fp32)
   __shared__ int reg[6];
-  __shared__ float4 rowrec[PCL_TR];
+  __shared__ __align__(16) float4 rowrec[PCL_TR];
   __shared__ uint64_t src_bar;
   __shared__ float lut[U8 ? C * 256 : 1];
-  __shared__ float tu[RT ? RT : 1];        // linspace(0,1,s) of the crop's columns (compile-time resolution only)
-  __shared__ float tv[RT ? PCL_TV : 1];    // ... and of the sub-block's intermediate rows
-  __shared__ __align__(16) float2 coltab[RT ? RT : 1];   // per output column: (weight of the upper tap, lower tap index) of the horizontal resize
+  __shared__ float tu[RT ? PCL_XB + 8 : 1];   // linspace(0,1,s) of the CTA's intermediate columns (compile-time resolution only)
+  __shared__ float tv[RT ? PCL_TV : 1];       // ... and of the sub-block's intermediate rows
+  __shared__ __align__(16) float2 coltab[RT ? PCL_XB : 1];   // per output column: (weight of the upper tap, lower tap byte offset in a mid4 row)
   const int q = blockIdx.y;
   const Crop c = load_crop(params + (size_t)q * PF);
   const int s = c.s;
-  const int Y0 = blockIdx.x * PCL_TR;
+  // CTA = (crop, PCL_TR output rows, one block of output columns): the column split halves the intermediate band and its
+  // source footprint, so band + staged tile fit the shared-memory budget of 5 CTAs/SM for every box up to the image size
+  const int yb = blockIdx.x / nxb, xb = blockIdx.x - yb * nxb;
+  const int xbw = RT ? PCL_XB : (((R + nxb - 1) / nxb + 1) & ~1);
+  const int X0 = xb * xbw, X1 = min(X0 + xbw, R) - 1;
+  const int Y0 = yb * PCL_TR;
   const int Y1 = min(Y0 + PCL_TR, R) - 1;
   const int plane = R * R;
   const SrcT* src = img + (size_t)(q / crops_per_img) * C * plane;
@@ -440,6 +447,14 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
   const float Rf = (float)R;
   const float rcpR = __fdiv_rn(1.0f, Rf);
   const int tid = threadIdx.x;
+  int ilo, ihi;
+  {
+    int t0, t1;
+    float l0, l1;
+    resize_coef(c, X0, R, ilo, t1, l0, l1);
+    resize_coef(c, X1, R, t0, ihi, l0, l1);
+  }
+  const int ncol = ihi - ilo + 1;   // intermediate columns this CTA needs
   if (U8) {
     for (int e = tid; e < C * 256; e += PCL_THREADS) {
       const int ch = e >> 8;
@@ -447,21 +462,24 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
     }
   }
   if (RT) {
-    for (int i = tid; i < s && i < RT; i += PCL_THREADS) tu[i] = lin01(c, i);
-    for (int x = tid; x < RT; x += PCL_THREADS) {
+    if (tid < ncol && tid < PCL_XB + 8) tu[tid] = lin01(c, ilo + tid);
+    if (tid >= 128 && tid - 128 <= X1 - X0) {
       int b0, b1;
       float lx0, lx1;
-      resize_coef(c, x, R, b0, b1, lx0, lx1);
-      coltab[x] = make_float2(lx1, __int_as_float(b0));   // lx0 = 1 - lx1 and b1 = b0 + (b0 < s-1) are recomputed exactly
+      resize_coef(c, X0 + tid - 128, R, b0, b1, lx0, lx1);
+      coltab[tid - 128] = make_float2(lx1, __int_as_float((b0 - ilo) * 16));   // lx0 = 1 - lx1, b1 = b0 + (b0 < s-1): recomputed exactly
     }
   }
+  // rows per sub-block: the band (16 B per intermediate pixel) plus the estimated source tile must fit
   int rows_sub = PCL_TR;
-  while (rows_sub > 1 && ((int)ceilf((float)rows_sub * c.scale) + 3) * s * 16 > smem_bytes) rows_sub >>= 1;
-  const bool fits = ((int)ceilf((float)rows_sub * c.scale) + 3) * s * 16 <= smem_bytes;
+  auto band_rows = [&](int rs) { return (int)ceilf((float)rs * c.scale) + 3; };
+  auto need = [&](int rs) { const int nr = band_rows(rs); return nr * ncol * 16 + C * (nr + 5) * ((ncol + 11) & ~3) * 4; };
+  while (rows_sub > 1 && need(rows_sub) > smem_bytes) rows_sub >>= 1;
+  const bool fits = band_rows(rows_sub) * ncol * 16 <= smem_bytes && ncol <= (RT ? PCL_XB + 8 : 1 << 30);
   if (s <= R && fits) {
     if (tid == 0) { mbar_init(&src_bar, 1); mbar_fence_init(); }
     int nuse = 0;
-    const int q256 = PCL_THREADS / s, r256 = PCL_THREADS - q256 * s;   // idx += 256  <=>  (row += q256, col += r256) with one carry
+    const int q256 = PCL_THREADS / ncol, r256 = PCL_THREADS - q256 * ncol;   // idx += 256  <=>  (row += q256, col += r256) with one carry
     for (int y0 = Y0; y0 <= Y1; y0 += rows_sub) {
       const int y1 = min(y0 + rows_sub - 1, Y1);
       int jlo, jhi, t0, t1;
@@ -469,16 +487,16 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
       resize_coef(c, y0, R, jlo, t1, l0, l1);
       resize_coef(c, y1, R, t0, jhi, l0, l1);
       const int nrows = jhi - jlo + 1;
-      const int n = nrows * s;
+      const int n = nrows * ncol;
       float* stile = reinterpret_cast<float*>(mid4 + n);   // source tile [C][rows][cols] fp32, cols a multiple of 4
       if (tid < 32) {
-        // The band's sample positions are the image of a rectangle of the intermediate grid under a homography: a convex
+        // The block's sample positions are the image of a rectangle of the intermediate grid under a homography: a convex
         // quad whose corner box (+ the bilinear margin) bounds every tap.  The tile spans that box in UNCLAMPED image
         // coordinates, at most [-1, R]: the parts outside the image are the reference's zero padding, so the gather needs
         // neither bounds predicates nor clamps.  fp32 images: warp 0 issues one TMA bulk copy per (channel, in-image row).
         const int lane = tid;
         float cx = 0.f, cy = 0.f;
-        if (lane < 4) sample_pos_uv(c, lin01(c, (lane & 1) ? s - 1 : 0), lin01(c, (lane >> 1) ? jhi : jlo), Rf, rcpR, cx, cy);
+        if (lane < 4) sample_pos_uv(c, lin01(c, (lane & 1) ? ihi : ilo), lin01(c, (lane >> 1) ? jhi : jlo), Rf, rcpR, cx, cy);
         float xmn = lane < 4 ? cx : 3.0e38f, xmx = lane < 4 ? cx : -3.0e38f, ymn = lane < 4 ? cy : 3.0e38f, ymx = lane < 4 ? cy : -3.0e38f;
 #pragma unroll
         for (int m = 1; m < 4; m <<= 1) {
@@ -514,11 +532,11 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
           }
         }
       }
-      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this sub-block
+      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this sub-block (band-row byte offsets)
         int a0, a1;
         float ly0, ly1;
         resize_coef(c, y0 + tid - 32, R, a0, a1, ly0, ly1);
-        rowrec[tid - 32] = make_float4(ly0, ly1, __int_as_float((a0 - jlo) * s), __int_as_float((a1 - jlo) * s));
+        rowrec[tid - 32] = make_float4(ly0, ly1, __int_as_float((a0 - jlo) * ncol * 16), __int_as_float((a1 - jlo) * ncol * 16));
       }
       if (RT && tid >= 64 && tid - 64 < nrows && tid - 64 < PCL_TV) tv[tid - 64] = lin01(c, jlo + tid - 64);
       __syncthreads();   // region record, row table, linspace tables, barrier init (and the LUT) are visible
@@ -555,14 +573,14 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
       // gather: one pass, thread = intermediate pixel
       {
         int i = tid, jr = 0;
-        while (i >= s) { i -= s; ++jr; }
+        while (i >= ncol) { i -= ncol; ++jr; }
         const float xlo = (float)rx0, xhi = (float)(rx0 + rnc - 1), ylo = (float)ry0, yhi = (float)(ry0 + rnr - 1);
         const int toff = ry0 * rnc + rx0;
         const int chs = rnr * rnc;
         for (int idx = tid; idx < n; idx += PCL_THREADS) {
           float ix, iy;
           if (RT) sample_pos_uv(c, tu[i], tv[min(jr, PCL_TV - 1)], Rf, rcpR, ix, iy);
-          else sample_pos_uv(c, lin01(c, i), lin01(c, jlo + jr), Rf, rcpR, ix, iy);
+          else sample_pos_uv(c, lin01(c, ilo + i), lin01(c, jlo + jr), Rf, rcpR, ix, iy);
           float v[4];
           // both taps of each axis inside the tile?  (float compares: a NaN position fails them and takes the fallback)
           if (tiled && ix >= xlo && ix < xhi && iy >= ylo && iy < yhi) {
@@ -589,27 +607,34 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
           }
           mid4[idx] = make_float4(v[0], v[1], v[2], v[3]);
           i += r256; jr += q256;
-          if (i >= s) { i -= s; ++jr; }
+          if (i >= ncol) { i -= ncol; ++jr; }
         }
       }
       __syncthreads();
-      // separable resize: a thread owns two adjacent output columns of one half of the sub-block's rows
+      // separable resize: a thread owns two adjacent output columns of one quarter of the sub-block's rows; the two live
+      // intermediate rows, interpolated horizontally, stay in registers while consecutive output rows share them
       {
         const int nout = y1 - y0 + 1;
-        const int halfrows = (nout + 1) >> 1;
-        const int g = tid >> 7;
-        const int tA = g * halfrows, tB = min(tA + halfrows, nout);
-        for (int x = 2 * (tid & 127); x < R; x += 256) {
-          int b0[2], b1[2];
+        const int NG = RT ? 4 : 2;                 // row groups (64 / 128 threads each)
+        const int gthreads = PCL_THREADS / NG;
+        const int grows = (nout + NG - 1) / NG;
+        const int g = tid / gthreads, tg = tid - g * gthreads;
+        const int tA = g * grows, tB = min(tA + grows, nout);
+        const char* midb = reinterpret_cast<const char*>(mid4);
+        for (int x = X0 + 2 * tg; x <= X1; x += 2 * gthreads) {
+          int ob0[2], ob1[2];   // byte offsets of the two horizontal taps inside a band row
           float lx0[2], lx1[2];
           if (RT) {
-            const float4 ct = *reinterpret_cast<const float4*>(coltab + x);   // x even, R even: both columns in one 16-byte load
-            lx1[0] = ct.x; b0[0] = __float_as_int(ct.y); lx1[1] = ct.z; b0[1] = __float_as_int(ct.w);
+            const float4 ct = *reinterpret_cast<const float4*>(coltab + (x - X0));   // x - X0 even: both columns in one 16-byte load
+            lx1[0] = ct.x; ob0[0] = __float_as_int(ct.y); lx1[1] = ct.z; ob0[1] = __float_as_int(ct.w);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) { lx0[k] = __fsub_rn(1.0f, lx1[k]); b1[k] = b0[k] + (b0[k] < s - 1 ? 1 : 0); }
+            for (int k = 0; k < 2; ++k) { lx0[k] = __fsub_rn(1.0f, lx1[k]); ob1[k] = ob0[k] + (ob0[k] < (s - 1 - ilo) * 16 ? 16 : 0); }
           } else {
-            resize_coef(c, x, R, b0[0], b1[0], lx0[0], lx1[0]);
-            resize_coef(c, min(x + 1, R - 1), R, b0[1], b1[1], lx0[1], lx1[1]);
+            int b0, b1;
+            resize_coef(c, x, R, b0, b1, lx0[0], lx1[0]);
+            ob0[0] = (b0 - ilo) * 16; ob1[0] = (b1 - ilo) * 16;
+            resize_coef(c, min(x + 1, R - 1), R, b0, b1, lx0[1], lx1[1]);
+            ob0[1] = (b0 - ilo) * 16; ob1[1] = (b1 - ilo) * 16;
           }
           int cur0 = -1, cur1 = -1;
           float h0[2][4], h1[2][4];
@@ -617,10 +642,10 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
           for (int k = 0; k < 2; ++k)
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) { h0[k][ch] = 0.f; h1[k][ch] = 0.f; }
-          auto hrow = [&](int o, float (*h)[4]) {
+          auto hrow = [&](int ob, float (*h)[4]) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              const float4 a = mid4[o + b0[k]], b = mid4[o + b1[k]];
+              const float4 a = *reinterpret_cast<const float4*>(midb + ob + ob0[k]), b = *reinterpret_cast<const float4*>(midb + ob + ob1[k]);
               h[k][0] = fmaf(lx1[k], b.x, __fmul_rn(lx0[k], a.x));
               if (C > 1) h[k][1] = fmaf(lx1[k], b.y, __fmul_rn(lx0[k], a.y));
               if (C > 2) h[k][2] = fmaf(lx1[k], b.z, __fmul_rn(lx0[k], a.z));
@@ -628,7 +653,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
             }
           };
           float* op = dst + (size_t)(y0 + tA) * R + x;
-          const bool two = x + 1 < R;
+          const bool two = x + 1 <= X1;
 #pragma unroll 1
           for (int t = tA; t < tB; ++t, op += R) {
             const float4 rr = rowrec[t];
@@ -659,9 +684,10 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
   }
   // generic path (s > R, or an intermediate row that does not fit): the four intermediate pixels of every output pixel directly
   if (U8) __syncthreads();
-  const int npix = (Y1 - Y0 + 1) * R;
+  const int wcols = X1 - X0 + 1;
+  const int npix = (Y1 - Y0 + 1) * wcols;
   for (int idx = tid; idx < npix; idx += PCL_THREADS) {
-    const int yy = idx / R, x = idx - yy * R;
+    const int yy = idx / wcols, x = X0 + idx - yy * wcols;
     const int y = Y0 + yy;
     int a0, a1, b0, b1;
     float ly0, ly1, lx0, lx1;
@@ -1298,7 +1324,7 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   // shared-memory budget per CTA: 44 KB -> 5 CTAs/SM (measured on B200: 3.31 ms vs 4.24 ms at 72 KB / 3 CTAs per SM;
   // the kernel is issue/latency bound, occupancy pays).  One intermediate row must fit: R*16 bytes * 4 rows.  The 8-bit
   // variant keeps its normalisation table (C KB) in static shared memory on top.
-  size_t smem = (pcl_exact() && !U8 ? 44 : (U8 ? 41 - C : 41)) * 1024;   // the fast kernel keeps ~3 KB of tables in static shared memory
+  size_t smem = (pcl_exact() && !U8 ? 44 : (U8 ? 42 - C : 42)) * 1024;   // the fast kernel keeps ~2 KB of tables in static shared memory
   { const char* e = getenv("HB_PCL_FWD_SMEM_KB"); if (e) smem = (size_t)atoi(e) * 1024; }   // experiment knob
   if (smem < (size_t)R * 16 * 4) smem = (size_t)R * 16 * 4;
   if (smem > 200 * 1024) { set_error("hb_pcl_fwd: img_res too large for the staged kernel"); return HB_E_UNSUPPORTED; }
@@ -1307,6 +1333,7 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   if (want_tma < 0) { const char* e = getenv("HB_PCL_TMA"); want_tma = (e && e[0] == '0') ? 0 : 1; }
   const int tma_ok = want_tma && (R % (U8 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
   dim3 grid((R + PCL_TR - 1) / PCL_TR, n_crops);
+  const int nxb = (R == 224) ? 224 / PCL_XB : (R > 128 ? 2 : 1);   // column blocks per row band of the fast kernel
   if constexpr (!U8) {
     if (pcl_exact()) {
       auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
@@ -1319,7 +1346,8 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
   auto fast_kernel = (R == 224 && v2) ? pcl_fwd_fast_kernel<C, 224, SrcT, true> : (v2 ? pcl_fwd_fast_kernel<C, 0, SrcT, true> : pcl_fwd_fast_kernel<C, 0, SrcT, false>);
   HB_CUDA(cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fast_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, (int)smem, tma_ok, nrm);
+  grid.x *= nxb;
+  fast_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, (int)smem, tma_ok, nxb, nrm);
   g_launches++;
   return check_launch("pcl_fwd_fast_kernel");
 }
