@@ -416,37 +416,51 @@ __device__ __forceinline__ void gather_global(const SrcT* __restrict__ src, cons
 
 constexpr int PCL_TV = 40;   // rows of the per-sub-block linspace table (an intermediate band never has more: 16 * scale + 3, scale <= 1)
 
-constexpr int PCL_XB = 112;   // output columns per CTA of the fast forward (two column blocks at R = 224)
+constexpr int PCL_XB = 224;   // output columns per CTA of the fast forward at R = 224 (one column block; 112 = two blocks measured slower:
+                              // the phases between barriers get too short)
+constexpr int PCL_NSEG = 2;   // row segments per crop: a CTA walks the bands of one segment, so the per-crop set-up is paid once per 7 bands
+
+// idx / d for 0 <= idx < 2^16, 1 <= d <= 2^16, without an integer division (~20 instructions): float quotient + fix-up
+__device__ __forceinline__ int small_div(int idx, int d) {
+  int q = __float2int_rz(__fdividef((float)idx + 0.5f, (float)d));
+  const int r = idx - q * d;
+  if (r < 0) --q; else if (r >= d) ++q;
+  return q;
+}
 
 template <int C, int RT, typename SrcT, bool V2>   // V2: out is 8-byte aligned and R even -> 64-bit stores
-__global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT* __restrict__ img, const float* __restrict__ params, int crops_per_img, int R_arg,
-                                                                      float* __restrict__ out, int smem_bytes, int tma_ok, int nxb, PclNorm nrm) {
+__global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT* __restrict__ img, const float* __restrict__ params, int crops_per_img, unsigned cpi_mul,
+                                                                      int R_arg, float* __restrict__ out, int smem_bytes, int tma_ok, int nxb_arg, PclNorm nrm) {
   const int R = RT ? RT : R_arg;
   constexpr bool U8 = sizeof(SrcT) == 1;
-  extern __shared__ __align__(16) float4 mid4[];  // [nrows][ncol] pixels, channels in .x .y .z .w; then the staged source tile (fp32)
-  __shared__ int reg[6];
+  extern __shared__ __align__(16) float4 mid4[];  // [cap] band pixels, channels in .x .y .z .w; then the staged source tile (fp32)
+  __shared__ int reg[2][6];                       // tile record of the current / the next band
   __shared__ __align__(16) float4 rowrec[PCL_TR];
   __shared__ uint64_t src_bar;
   __shared__ float lut[U8 ? C * 256 : 1];
   __shared__ float tu[RT ? PCL_XB + 8 : 1];   // linspace(0,1,s) of the CTA's intermediate columns (compile-time resolution only)
-  __shared__ float tv[RT ? PCL_TV : 1];       // ... and of the sub-block's intermediate rows
-  __shared__ __align__(16) float2 coltab[RT ? PCL_XB : 1];   // per output column: (weight of the upper tap, lower tap byte offset in a mid4 row)
+  __shared__ float tv[RT ? PCL_TV : 1];       // ... and of the band's intermediate rows
+  __shared__ __align__(16) float2 coltab[RT ? PCL_XB : 1];   // per output column: (weight of the upper tap, lower tap byte offset in a band row)
   const int q = blockIdx.y;
   const Crop c = load_crop(params + (size_t)q * PF);
   const int s = c.s;
-  // CTA = (crop, PCL_TR output rows, one block of output columns): the column split halves the intermediate band and its
-  // source footprint, so band + staged tile fit the shared-memory budget of 5 CTAs/SM for every box up to the image size
-  const int yb = blockIdx.x / nxb, xb = blockIdx.x - yb * nxb;
+  // CTA = (crop, row segment, block of output columns).  The column split halves the intermediate band and its source
+  // footprint (band + staged tile fit the shared-memory budget of 5 CTAs/SM for every box up to the image size); walking
+  // the segment's bands in one CTA pays the per-crop set-up once and lets the next band's tile fly during the resize.
+  const int nxb = RT ? RT / PCL_XB : nxb_arg;
+  const int yseg = RT ? (int)(blockIdx.x / (RT / PCL_XB)) : (int)blockIdx.x / nxb, xb = blockIdx.x - yseg * nxb;
   const int xbw = RT ? PCL_XB : (((R + nxb - 1) / nxb + 1) & ~1);
+  const int segrows = RT ? ((RT / PCL_NSEG + PCL_TR - 1) / PCL_TR) * PCL_TR : (((R + PCL_NSEG - 1) / PCL_NSEG + PCL_TR - 1) / PCL_TR) * PCL_TR;
   const int X0 = xb * xbw, X1 = min(X0 + xbw, R) - 1;
-  const int Y0 = yb * PCL_TR;
-  const int Y1 = min(Y0 + PCL_TR, R) - 1;
+  const int Y0 = yseg * segrows;
+  const int Y1 = min(Y0 + segrows, R) - 1;
   const int plane = R * R;
-  const SrcT* src = img + (size_t)(q / crops_per_img) * C * plane;
+  const SrcT* src = img + (size_t)(cpi_mul ? __umulhi((unsigned)q, cpi_mul) : (unsigned)q) * C * plane;   // q / crops_per_img (0: one crop per image)
   float* dst = out + (size_t)q * C * plane;
   const float Rf = (float)R;
   const float rcpR = __fdiv_rn(1.0f, Rf);
   const int tid = threadIdx.x;
+  if (Y0 > Y1 || X0 > X1) return;
   int ilo, ihi;
   {
     int t0, t1;
@@ -463,86 +477,99 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
   }
   if (RT) {
     if (tid < ncol && tid < PCL_XB + 8) tu[tid] = lin01(c, ilo + tid);
-    if (tid >= 128 && tid - 128 <= X1 - X0) {
+    for (int x = tid; x <= X1 - X0; x += PCL_THREADS) {
       int b0, b1;
       float lx0, lx1;
-      resize_coef(c, X0 + tid - 128, R, b0, b1, lx0, lx1);
-      coltab[tid - 128] = make_float2(lx1, __int_as_float((b0 - ilo) * 16));   // lx0 = 1 - lx1, b1 = b0 + (b0 < s-1): recomputed exactly
+      resize_coef(c, X0 + x, R, b0, b1, lx0, lx1);
+      coltab[x] = make_float2(lx1, __int_as_float((b0 - ilo) * 16));   // lx0 = 1 - lx1, b1 = b0 + (b0 < s-1): recomputed exactly
     }
   }
-  // rows per sub-block: the band (16 B per intermediate pixel) plus the estimated source tile must fit
+  // rows per band: the band (16 B per intermediate pixel) must fit
   int rows_sub = PCL_TR;
   auto band_rows = [&](int rs) { return (int)ceilf((float)rs * c.scale) + 3; };
-  auto need = [&](int rs) { const int nr = band_rows(rs); return nr * ncol * 16 + C * (nr + 5) * ((ncol + 11) & ~3) * 4; };
-  while (rows_sub > 1 && need(rows_sub) > smem_bytes) rows_sub >>= 1;
-  const bool fits = band_rows(rows_sub) * ncol * 16 <= smem_bytes && ncol <= (RT ? PCL_XB + 8 : 1 << 30);
+  // (the band alone decides: a tile that does not fit beside it is gathered through L1/L2 instead -- shrinking the band until
+  //  band + tile fit measured slower, 491 vs 401 us per 2048 crops: shorter phases between barriers, more halo rows)
+  while (rows_sub > 1 && band_rows(rows_sub) * ncol * 16 > smem_bytes) rows_sub >>= 1;
+  const int cap = band_rows(rows_sub) * ncol;          // band capacity in pixels; the tile lives behind it
+  const bool fits = cap * 16 <= smem_bytes && ncol <= (RT ? PCL_XB + 8 : 1 << 30);
   if (s <= R && fits) {
+    float* stile = reinterpret_cast<float*>(mid4 + cap);   // source tile [C][rows][cols] fp32, cols a multiple of 4
+    const int tile_bytes = smem_bytes - cap * 16;
+    // warp 0: tile record of the band starting at output row y0 (+ the TMA bulk copies for an fp32 image)
+    auto issue_tile = [&](int y0, int slot) {
+      // The band's sample positions are the image of a rectangle of the intermediate grid under a homography: a convex
+      // quad whose corner box (+ the bilinear margin) bounds every tap.  The tile spans that box in UNCLAMPED image
+      // coordinates, at most [-1, R]: the parts outside the image are the reference's zero padding, so the gather needs
+      // neither bounds predicates nor clamps.  fp32 images: one TMA bulk copy per (channel, in-image row).
+      const int lane = tid;
+      const int y1 = min(y0 + rows_sub - 1, Y1);
+      int jlo, jhi, t0, t1;
+      float l0, l1;
+      resize_coef(c, y0, R, jlo, t1, l0, l1);
+      resize_coef(c, y1, R, t0, jhi, l0, l1);
+      float cx = 0.f, cy = 0.f;
+      if (lane < 4) sample_pos_uv(c, lin01(c, (lane & 1) ? ihi : ilo), lin01(c, (lane >> 1) ? jhi : jlo), Rf, rcpR, cx, cy);
+      float xmn = lane < 4 ? cx : 3.0e38f, xmx = lane < 4 ? cx : -3.0e38f, ymn = lane < 4 ? cy : 3.0e38f, ymx = lane < 4 ? cy : -3.0e38f;
+#pragma unroll
+      for (int m = 1; m < 4; m <<= 1) {
+        xmn = fminf(xmn, __shfl_xor_sync(0xffffffffu, xmn, m)); xmx = fmaxf(xmx, __shfl_xor_sync(0xffffffffu, xmx, m));
+        ymn = fminf(ymn, __shfl_xor_sync(0xffffffffu, ymn, m)); ymx = fmaxf(ymx, __shfl_xor_sync(0xffffffffu, ymx, m));
+      }
+      xmn = __shfl_sync(0xffffffffu, xmn, 0); xmx = __shfl_sync(0xffffffffu, xmx, 0);
+      ymn = __shfl_sync(0xffffffffu, ymn, 0); ymx = __shfl_sync(0xffffffffu, ymx, 0);
+      int use = 0, bx0 = 0, by0 = 0, ncols = 0, nr = 0;
+      if (tma_ok && xmn == xmn && xmx == xmx && ymn == ymn && ymx == ymx && xmx > -2.0f && ymx > -2.0f && xmn < Rf + 1.0f && ymn < Rf + 1.0f) {
+        const int xl = max(-1, (int)floorf(fmaxf(xmn, -4.0f)) - 1), xh = min(R, (int)floorf(fminf(xmx, Rf + 4.0f)) + 2);
+        const int yl = max(-1, (int)floorf(fmaxf(ymn, -4.0f)) - 1), yh = min(R, (int)floorf(fminf(ymx, Rf + 4.0f)) + 2);
+        bx0 = xl & ~3;                      // two's complement: -1 -> -4
+        ncols = (xh - bx0 + 4) & ~3;
+        by0 = yl;
+        nr = yh - yl + 1;
+        use = nr > 0 && ncols > 0 && C * nr * ncols * 4 <= tile_bytes;
+      }
+      const int cx0 = max(bx0, 0), cx1 = min(bx0 + ncols, R);        // in-image column range (multiples of 4)
+      const int ry0 = max(by0, 0), ry1 = min(by0 + nr, R);           // in-image row range
+      const int pad = use && (bx0 < 0 || bx0 + ncols > R || by0 < 0 || by0 + nr > R);
+      if (lane == 0) {
+        reg[slot][0] = bx0; reg[slot][1] = by0; reg[slot][2] = ncols; reg[slot][3] = nr; reg[slot][4] = use; reg[slot][5] = pad;
+        if (use && !U8) mbar_arrive_expect_tx(&src_bar, (uint32_t)(C * (ry1 - ry0) * (cx1 - cx0) * 4));
+      }
+      __syncwarp();
+      if (use && !U8) {
+        fence_proxy_async();   // the previous band's generic-proxy accesses to the tile area are ordered before these copies
+        const int nrin = ry1 - ry0;
+        for (int k = lane; k < C * nrin; k += 32) {
+          const int ch = small_div(k, nrin), r = ry0 + (k - ch * nrin);
+          bulk_g2s(stile + ((size_t)(ch * nr + (r - by0)) * ncols + (cx0 - bx0)),
+                   reinterpret_cast<const float*>(src) + (size_t)ch * plane + (size_t)r * R + cx0, (uint32_t)((cx1 - cx0) * 4), &src_bar);
+        }
+      }
+    };
     if (tid == 0) { mbar_init(&src_bar, 1); mbar_fence_init(); }
-    int nuse = 0;
-    const int q256 = PCL_THREADS / ncol, r256 = PCL_THREADS - q256 * ncol;   // idx += 256  <=>  (row += q256, col += r256) with one carry
-    for (int y0 = Y0; y0 <= Y1; y0 += rows_sub) {
+    __syncwarp();
+    if (tid < 32) issue_tile(Y0, 0);
+    int nuse = 0, slot = 0;
+    const int q256 = small_div(PCL_THREADS, ncol), r256 = PCL_THREADS - q256 * ncol;   // idx += 256  <=>  (row += q256, col += r256) with one carry
+    for (int y0 = Y0; y0 <= Y1; y0 += rows_sub, slot ^= 1) {
       const int y1 = min(y0 + rows_sub - 1, Y1);
       int jlo, jhi, t0, t1;
       float l0, l1;
       resize_coef(c, y0, R, jlo, t1, l0, l1);
       resize_coef(c, y1, R, t0, jhi, l0, l1);
       const int nrows = jhi - jlo + 1;
-      const int n = nrows * ncol;
-      float* stile = reinterpret_cast<float*>(mid4 + n);   // source tile [C][rows][cols] fp32, cols a multiple of 4
-      if (tid < 32) {
-        // The block's sample positions are the image of a rectangle of the intermediate grid under a homography: a convex
-        // quad whose corner box (+ the bilinear margin) bounds every tap.  The tile spans that box in UNCLAMPED image
-        // coordinates, at most [-1, R]: the parts outside the image are the reference's zero padding, so the gather needs
-        // neither bounds predicates nor clamps.  fp32 images: warp 0 issues one TMA bulk copy per (channel, in-image row).
-        const int lane = tid;
-        float cx = 0.f, cy = 0.f;
-        if (lane < 4) sample_pos_uv(c, lin01(c, (lane & 1) ? ihi : ilo), lin01(c, (lane >> 1) ? jhi : jlo), Rf, rcpR, cx, cy);
-        float xmn = lane < 4 ? cx : 3.0e38f, xmx = lane < 4 ? cx : -3.0e38f, ymn = lane < 4 ? cy : 3.0e38f, ymx = lane < 4 ? cy : -3.0e38f;
-#pragma unroll
-        for (int m = 1; m < 4; m <<= 1) {
-          xmn = fminf(xmn, __shfl_xor_sync(0xffffffffu, xmn, m)); xmx = fmaxf(xmx, __shfl_xor_sync(0xffffffffu, xmx, m));
-          ymn = fminf(ymn, __shfl_xor_sync(0xffffffffu, ymn, m)); ymx = fmaxf(ymx, __shfl_xor_sync(0xffffffffu, ymx, m));
-        }
-        xmn = __shfl_sync(0xffffffffu, xmn, 0); xmx = __shfl_sync(0xffffffffu, xmx, 0);
-        ymn = __shfl_sync(0xffffffffu, ymn, 0); ymx = __shfl_sync(0xffffffffu, ymx, 0);
-        int use = 0, bx0 = 0, by0 = 0, ncols = 0, nr = 0;
-        if (tma_ok && xmn == xmn && xmx == xmx && ymn == ymn && ymx == ymx && xmx > -2.0f && ymx > -2.0f && xmn < Rf + 1.0f && ymn < Rf + 1.0f) {
-          const int xl = max(-1, (int)floorf(fmaxf(xmn, -4.0f)) - 1), xh = min(R, (int)floorf(fminf(xmx, Rf + 4.0f)) + 2);
-          const int yl = max(-1, (int)floorf(fmaxf(ymn, -4.0f)) - 1), yh = min(R, (int)floorf(fminf(ymx, Rf + 4.0f)) + 2);
-          bx0 = xl & ~3;                      // two's complement: -1 -> -4
-          ncols = (xh - bx0 + 4) & ~3;
-          by0 = yl;
-          nr = yh - yl + 1;
-          use = nr > 0 && ncols > 0 && (size_t)n * 16 + (size_t)C * nr * ncols * 4 <= (size_t)smem_bytes;
-        }
-        const int cx0 = max(bx0, 0), cx1 = min(bx0 + ncols, R);        // in-image column range (multiples of 4)
-        const int ry0 = max(by0, 0), ry1 = min(by0 + nr, R);           // in-image row range
-        const int pad = use && (bx0 < 0 || bx0 + ncols > R || by0 < 0 || by0 + nr > R);
-        if (lane == 0) {
-          reg[0] = bx0; reg[1] = by0; reg[2] = ncols; reg[3] = nr; reg[4] = use; reg[5] = pad;
-          if (use && !U8) mbar_arrive_expect_tx(&src_bar, (uint32_t)(C * (ry1 - ry0) * (cx1 - cx0) * 4));
-        }
-        __syncwarp();
-        if (use && !U8) {
-          const int nrin = ry1 - ry0;
-          for (int k = lane; k < C * nrin; k += 32) {
-            const int ch = k / nrin, r = ry0 + (k - ch * nrin);
-            bulk_g2s(stile + ((size_t)(ch * nr + (r - by0)) * ncols + (cx0 - bx0)),
-                     reinterpret_cast<const float*>(src) + (size_t)ch * plane + (size_t)r * R + cx0, (uint32_t)((cx1 - cx0) * 4), &src_bar);
-          }
-        }
-      }
-      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this sub-block (band-row byte offsets)
+      const int n = nrows * ncol;                      // <= cap
+      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this band (band-row byte offsets)
         int a0, a1;
         float ly0, ly1;
         resize_coef(c, y0 + tid - 32, R, a0, a1, ly0, ly1);
         rowrec[tid - 32] = make_float4(ly0, ly1, __int_as_float((a0 - jlo) * ncol * 16), __int_as_float((a1 - jlo) * ncol * 16));
       }
       if (RT && tid >= 64 && tid - 64 < nrows && tid - 64 < PCL_TV) tv[tid - 64] = lin01(c, jlo + tid - 64);
-      __syncthreads();   // region record, row table, linspace tables, barrier init (and the LUT) are visible
-      const int rx0 = reg[0], ry0 = reg[1], rnc = reg[2], rnr = reg[3];
-      const bool tiled = reg[4] != 0;
-      if (tiled && (U8 || reg[5])) {
+      __syncthreads();   // tile record, row table, linspace tables, barrier init (and the LUT) are visible
+      const int rx0 = reg[slot][0], ry0 = reg[slot][1], rnc = reg[slot][2], rnr = reg[slot][3];
+      const bool tiled = reg[slot][4] != 0;
+      const bool padded = reg[slot][5] != 0;
+      if (tiled && (U8 || padded)) {
         // 8-bit image: the threads stage the tile themselves, 4 pixels per 32-bit load, normalised through the table,
         // out-of-image groups zero.  fp32 image: only the out-of-image groups are written (the bulk copies fill the rest).
         const int nc4 = rnc >> 2;
@@ -550,7 +577,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
         const float inv_nc4 = 1.0f / (float)nc4;
         for (int e = tid; e < tot; e += PCL_THREADS) {
           const int rowi = fast_div(e, nc4, inv_nc4), c4 = e - rowi * nc4;   // rowi = ch * rnr + r
-          const int ch = rowi / rnr, r = rowi - ch * rnr;
+          const int ch = small_div(rowi, rnr), r = rowi - ch * rnr;
           const int y = ry0 + r, x = rx0 + 4 * c4;
           const bool inside = y >= 0 && y < R && x >= 0 && x < R;            // x, R multiples of 4: a group is all in or all out
           float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -568,12 +595,11 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
       }
       if (tiled) {
         if (U8) __syncthreads();
-        else { mbar_wait(&src_bar, nuse & 1); ++nuse; if (reg[5]) __syncthreads(); }
+        else { mbar_wait(&src_bar, nuse & 1); ++nuse; if (padded) __syncthreads(); }
       }
       // gather: one pass, thread = intermediate pixel
       {
-        int i = tid, jr = 0;
-        while (i >= ncol) { i -= ncol; ++jr; }
+        int jr = small_div(tid, ncol), i = tid - jr * ncol;
         const float xlo = (float)rx0, xhi = (float)(rx0 + rnc - 1), ylo = (float)ry0, yhi = (float)(ry0 + rnr - 1);
         const int toff = ry0 * rnc + rx0;
         const int chs = rnr * rnc;
@@ -610,15 +636,18 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
           if (i >= ncol) { i -= ncol; ++jr; }
         }
       }
-      __syncthreads();
-      // separable resize: a thread owns two adjacent output columns of one quarter of the sub-block's rows; the two live
+      __syncthreads();   // the band is complete; the tile is free
+      // the next band's tile flies while this band is resized: warp 0 is the producer, warps 1..7 resize
+      if (tid < 32 && y0 + rows_sub <= Y1) issue_tile(y0 + rows_sub, slot ^ 1);
+      // separable resize: a thread owns two adjacent output columns of one group of the band's rows; the two live
       // intermediate rows, interpolated horizontally, stay in registers while consecutive output rows share them
-      {
+      if (tid >= 32) {
         const int nout = y1 - y0 + 1;
-        const int NG = RT ? 4 : 2;                 // row groups (64 / 128 threads each)
-        const int gthreads = PCL_THREADS / NG;
+        const int rt = tid - 32;                                   // 224 resize threads
+        const int gthreads = (PCL_THREADS - 32) / 2;               // two row groups of 112 threads (112 column pairs at R = 224)
+        const int NG = 2;
         const int grows = (nout + NG - 1) / NG;
-        const int g = tid / gthreads, tg = tid - g * gthreads;
+        const int g = rt >= gthreads ? 1 : 0, tg = rt - g * gthreads;
         const int tA = g * grows, tB = min(tA + grows, nout);
         const char* midb = reinterpret_cast<const char*>(mid4);
         for (int x = X0 + 2 * tg; x <= X1; x += 2 * gthreads) {
@@ -678,7 +707,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
           }
         }
       }
-      __syncthreads();   // end of the sub-block: the tile, the tables and the region record are reused
+      __syncthreads();   // end of the band: the band buffer, the row tables and this band's tile record are reused
     }
     return;
   }
@@ -1324,7 +1353,7 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   // shared-memory budget per CTA: 44 KB -> 5 CTAs/SM (measured on B200: 3.31 ms vs 4.24 ms at 72 KB / 3 CTAs per SM;
   // the kernel is issue/latency bound, occupancy pays).  One intermediate row must fit: R*16 bytes * 4 rows.  The 8-bit
   // variant keeps its normalisation table (C KB) in static shared memory on top.
-  size_t smem = (pcl_exact() && !U8 ? 44 : (U8 ? 42 - C : 42)) * 1024;   // the fast kernel keeps ~2 KB of tables in static shared memory
+  size_t smem = (pcl_exact() && !U8 ? 44 : (U8 ? 41 - C : 41)) * 1024;   // the fast kernel keeps ~3 KB of tables in static shared memory
   { const char* e = getenv("HB_PCL_FWD_SMEM_KB"); if (e) smem = (size_t)atoi(e) * 1024; }   // experiment knob
   if (smem < (size_t)R * 16 * 4) smem = (size_t)R * 16 * 4;
   if (smem > 200 * 1024) { set_error("hb_pcl_fwd: img_res too large for the staged kernel"); return HB_E_UNSUPPORTED; }
@@ -1333,7 +1362,8 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   if (want_tma < 0) { const char* e = getenv("HB_PCL_TMA"); want_tma = (e && e[0] == '0') ? 0 : 1; }
   const int tma_ok = want_tma && (R % (U8 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
   dim3 grid((R + PCL_TR - 1) / PCL_TR, n_crops);
-  const int nxb = (R == 224) ? 224 / PCL_XB : (R > 128 ? 2 : 1);   // column blocks per row band of the fast kernel
+  const int nxb = (R == 224) ? 224 / PCL_XB : (R > 128 ? 2 : 1);   // column blocks of the fast kernel
+  const unsigned cpi_mul = (unsigned)((0x100000000ull + (unsigned)crops_per_img - 1) / (unsigned)crops_per_img);   // q / cpi == umulhi(q, cpi_mul) for q * cpi < 2^32
   if constexpr (!U8) {
     if (pcl_exact()) {
       auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
@@ -1346,8 +1376,9 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
   auto fast_kernel = (R == 224 && v2) ? pcl_fwd_fast_kernel<C, 224, SrcT, true> : (v2 ? pcl_fwd_fast_kernel<C, 0, SrcT, true> : pcl_fwd_fast_kernel<C, 0, SrcT, false>);
   HB_CUDA(cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  grid.x *= nxb;
-  fast_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, (int)smem, tma_ok, nxb, nrm);
+  if (crops_per_img > 1 && (unsigned long long)n_crops * (unsigned)crops_per_img >= 0x100000000ull) { set_error("hb_pcl_fwd: n_crops * crops_per_img must be below 2^32"); return HB_E_ARG; }
+  grid.x = PCL_NSEG * nxb;
+  fast_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, crops_per_img == 1 ? 0u : cpi_mul, R, out, (int)smem, tma_ok, nxb, nrm);
   g_launches++;
   return check_launch("pcl_fwd_fast_kernel");
 }
