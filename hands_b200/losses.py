@@ -84,9 +84,8 @@ class VectorLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, pred_minus, pred2, gt, gt_minus, valid, valid2, gate):
         lib = _lib.load()
-        B = pred.shape[0]
-        D = pred[0].numel() if B else int(torch.tensor(pred.shape[1:]).prod())
-        f = lambda t, n: None if t is None else _f32c(t.reshape(B, D), n, (B, D))  # noqa: E731
+        B, D = pred.shape   # (B, D) views are made by the caller, so autograd sees the gradient in the shape it gave
+        f = lambda t, n: None if t is None else _f32c(t, n, (B, D))  # noqa: E731
         pred, pred_minus, pred2, gt, gt_minus = f(pred, "pred"), f(pred_minus, "pred_minus"), f(pred2, "pred2"), f(gt, "gt"), f(gt_minus, "gt_minus")
         valid, valid2, gate = _f32c(valid, "valid", (B,)), _f32c(valid2, "valid2", (B,)), _f32c(gate, "gate", (B,))
         dev = pred.device
@@ -122,9 +121,9 @@ def vector_loss(pred, gt, valid=None, gate=None, pred2=None, pred_minus=None, gt
     src/utils/loss_modules.py:99-113): returns the scalar the reference calls `loss_*.mean()`.  Shapes (B, ...) with equal
     trailing sizes; `pred2` is a second prediction scored against the same target (cam_t.wp.init); `pred_minus`/`gt_minus`
     are subtracted first (the relative translation l - r); valid/valid2/gate are (B,) masks."""
-    shape = pred.shape
-    v = lambda t: None if t is None else t.reshape(shape)  # noqa: E731
-    return VectorLossFunction.apply(pred, v(pred_minus), v(pred2), gt.reshape(shape), v(gt_minus), valid, valid2, gate)
+    B = pred.shape[0]
+    v = lambda t: None if t is None else t.reshape(B, -1)  # noqa: E731
+    return VectorLossFunction.apply(v(pred), v(pred_minus), v(pred2), v(gt), v(gt_minus), valid, valid2, gate)
 
 
 def axis_angle_to_matrix(aa):
