@@ -734,3 +734,28 @@ def test_mano_decimator_gpu(dev, golden_dir):
     dec = MANODecimator(data={"D_right": g["D_right"], "D_left": g["D_left"]})
     out = dec.downsample(torch.from_numpy(g["verts"]).to(dev), True)
     tol_check("decimator", rel(out, torch.from_numpy(g["sub_r"])), 1e-5)   # cuBLAS may use TF32-free fp32 here; 1e-5 relative
+
+
+def test_pcl_more_than_65535_crops(dev):
+    """C4's true shard at 2 GPUs is 32,768 samples = 65,536 crops per launch: crops live on grid.x (no 65,535 limit).
+    Small images so the batch stays light; a slice recomputed on its own must match bit for bit, forward and backward."""
+    from hands_b200.pcl import perspective_crop
+
+    res, n = 32, 66000
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(n, 1, res, res, generator=g).to(dev)
+    side = torch.randint(8, 25, (n,), generator=g)
+    x0 = torch.randint(0, res - 25, (n,), generator=g)
+    y0 = torch.randint(0, res - 25, (n,), generator=g)
+    bbox = torch.stack([x0, y0, x0 + side, y0 + side], dim=1).int().to(dev)
+    K = torch.tensor([[60.0, 0, 16], [0, 60.0, 16], [0, 0, 1]]).expand(n, 3, 3).contiguous().to(dev)
+    w = torch.randn(n, 1, res, res, generator=g).to(dev)
+    x = img.clone().requires_grad_(True)
+    crop, _ = perspective_crop(x, bbox, K, img_res=res)
+    (gx,) = torch.autograd.grad((crop * w).sum(), x)
+    sl = slice(65500, 65900)
+    xs = img[sl].clone().requires_grad_(True)
+    cs, _ = perspective_crop(xs, bbox[sl], K[sl], img_res=res)
+    (gs,) = torch.autograd.grad((cs * w[sl]).sum(), xs)
+    assert torch.equal(cs, crop[sl]) and torch.equal(gs, gx[sl])
+    assert float(crop[-1].abs().max()) > 0
