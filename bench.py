@@ -182,7 +182,7 @@ def run_ours(args, rank, world, local_rank):
     metrics_vec = torch.zeros(64, device=dev)
 
     def one_step():
-        step.run(overlap=not args.no_overlap)
+        step.run()
         if world > 1:
             dist.all_reduce(metrics_vec)   # packed metric scalars (north_star); no data-path collective
 
@@ -232,7 +232,6 @@ def run_ours(args, rank, world, local_rank):
         t_bwd = cuda_time(step.pcl_backward, reps, 2, dev)
         t_mf = cuda_time(lambda: [step.mano_forward(0), step.mano_forward(1)], reps, 2, dev)
         t_mb = cuda_time(lambda: [step.mano_backward(0), step.mano_backward(1)], reps, 2, dev)
-        t_seq = cuda_time(lambda: step.run(overlap=False), reps, 2, dev)
         b_fwd = n * (plane + 12.0 * step.mean_s2)
         b_bwd = n * plane + S * plane
         fam = {
@@ -244,9 +243,9 @@ def run_ours(args, rank, world, local_rank):
                                                                         "frac": 2 * S * 11048.0 / t_mb / 1e9 / peak, "hands_per_s": 2 * S / t_mb},
         }
         fused_ms = elapsed / args.steps * 1e3
-        overlap = {"fused_ms": fused_ms, "single_stream_ms": t_seq * 1e3, "sum_of_families_ms": (t_fwd + t_bwd + t_mf + t_mb) * 1e3,
+        overlap = {"fused_ms": fused_ms, "sum_of_families_ms": (t_fwd + t_bwd + t_mf + t_mb) * 1e3,
                    "pcl_alone_ms": (t_fwd + t_bwd) * 1e3, "mano_alone_ms": (t_mf + t_mb) * 1e3,
-                   "mano_exposed_ms": fused_ms - (t_fwd + t_bwd) * 1e3}
+                   "note": "one stream: the PCL kernels fill the register file, no MANO CTA can be co-resident (hands_b200/step.py)"}
         Sk = min(S, 1024)
         ks = step if S == Sk else GeometryStep(Sk, dev, img_res=IMG_RES, seed=7)
         ks.pcl_setup()
@@ -317,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
                    "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
-                   "streams": "pcl || mano" if not args.no_overlap else "single",
+                   "streams": "single",
                    "pcl_forward": "exact (torch op order)" if os.environ.get("HB_PCL_EXACT", "0") == "1" else "default (reference sample positions, separable resize)",
                    "mano_contractions": "tcgen05 3xTF32" if os.environ.get("HB_MANO_TC", "1") != "0" else "ffma"},
         "clocks": clocks,
@@ -442,7 +441,7 @@ def run_e2e(step, args, dev, world, barrier, src_u8=True, steps=None):
                     d.copy_(hb[c], non_blocking=True)
                 ready[k].record(copy_stream)
             cur.wait_event(ready[k])
-            gs.run(overlap=not args.no_overlap)
+            gs.run()
             consumed[k].record(cur)
             for hb, o in zip(host_out, dev_outputs(gs)):
                 hb[c].copy_(o, non_blocking=True)
@@ -482,7 +481,6 @@ def main():
     ap.add_argument("--samples", type=int, default=8192, help="samples per GPU per step (C4: 65536 / 8)")
     ap.add_argument("--ref-samples", type=int, default=256, help="samples per CPU-reference step (bounded sample)")
     ap.add_argument("--e2e-chunk", type=int, default=1024, help="samples per pipelined e2e chunk")
-    ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the side legs (other configs, fp32-source e2e, CPU worker pool)")

@@ -1,16 +1,15 @@
-"""Pre-allocated, stream-overlapped geometry step: the fast path a training loop (and bench.py) drives.
+"""Pre-allocated geometry step: the fast path a training loop (and bench.py) drives.
 
 One `GeometryStep` owns every buffer of a two-hand sample batch on one GPU and runs
 
-    PCL setup -> PCL forward (2 crops / sample, one shared source image)        stream "pcl"
+    PCL setup -> PCL forward (2 crops / sample, one shared source image)
     MANO head forward right + left  (global orientation pre-rotated by R_virt2orig,
-        hands_light/model.py:330-334, fused as `pre_rot`)                        stream "mano"
-    MANO head backward right + left                                             stream "mano"
-    PCL backward                                                                stream "pcl"
+        hands_light/model.py:330-334, fused as `pre_rot`)
+    MANO head backward right + left
+    PCL backward
 
-through the C ABI, with no allocation and no autograd bookkeeping inside the step.  The two streams
-overlap the FFMA-bound MANO kernels with the HBM-bound PCL kernels.  The autograd drop-ins in
-`hands_b200.functional` call the same entry points; this class only removes the per-call allocations.
+through the C ABI on the current stream, with no allocation and no autograd bookkeeping inside the step.  The autograd
+drop-ins in `hands_b200.functional` call the same entry points; this class only removes the per-call allocations.
 """
 import ctypes
 import os
@@ -36,13 +35,6 @@ class GeometryStep:
         self.grads_on = grads_on
         S, R, dev = self.S, self.R, self.dev
         f32 = dict(dtype=torch.float32, device=dev)
-        self.s_pcl = torch.cuda.Stream(device=dev)
-        # equal priority measured best on B200 (16.60 ms vs 16.75 ms with the MANO stream at -1)
-        self.s_mano = torch.cuda.Stream(device=dev, priority=int(os.environ.get("HB_MANO_STREAM_PRIORITY", "0")))
-        self.ev_setup = torch.cuda.Event()
-        self.ev_start = torch.cuda.Event()
-        self.ev_pcl_done = torch.cuda.Event()
-        self.ev_mano_done = torch.cuda.Event()
         n = S * hands_per_sample  # crops == hands
         self.n = n
         gen = torch.Generator(device=dev).manual_seed(seed)
@@ -134,15 +126,14 @@ class GeometryStep:
                                              self.mano_ws_bytes, self._st()), "hb_mano_head_bwd")
 
     # ---- the fused step ----------------------------------------------------------------------------
-    def run(self, overlap=True):
-        """Enqueue one full fwd+bwd step.  Work is ordered after everything already on the current
-        stream and the current stream waits for it, so callers can bracket it with events."""
-        with torch.cuda.device(self.dev):   # launches and cudaFuncSetAttribute target self.dev whatever the caller's device
-            self._run(overlap)
+    def run(self):
+        """Enqueue one full fwd+bwd step on the current stream.
 
-    def _run(self, overlap):
-        cur = torch.cuda.current_stream(self.dev)
-        if not overlap or not (self.with_pcl and self.with_mano):
+        One stream on purpose.  Round 1 ran MANO on a second stream "overlapped" with the crop layer; measured, the fused
+        step took exactly the sum of its families (10.84 vs 10.87 ms): every PCL kernel fills the register file (5 x 256 x 48,
+        3 x 256 x 80, 4 x 256 x 62 registers per SM), so no MANO CTA can become resident beside one, whatever the stream
+        priorities -- the second stream only queued.  The MANO share is cut in the kernels instead."""
+        with torch.cuda.device(self.dev):   # launches and cudaFuncSetAttribute target self.dev whatever the caller's device
             if self.with_pcl:
                 self.pcl_setup()
                 self.pcl_forward()
@@ -155,26 +146,6 @@ class GeometryStep:
                     self.mano_backward(side)
             if self.with_pcl:
                 self.pcl_backward()
-            return
-        self.ev_start.record(cur)
-        self.s_pcl.wait_event(self.ev_start)
-        self.s_mano.wait_event(self.ev_start)
-        with torch.cuda.stream(self.s_pcl):
-            self.pcl_setup()
-            self.ev_setup.record(self.s_pcl)
-            self.pcl_forward()
-            self.pcl_backward()
-            self.ev_pcl_done.record(self.s_pcl)
-        with torch.cuda.stream(self.s_mano):
-            self.s_mano.wait_event(self.ev_setup)
-            self.gather_pre_rot()
-            for side in range(self.hps):
-                self.mano_forward(side)
-            for side in range(self.hps):
-                self.mano_backward(side)
-            self.ev_mano_done.record(self.s_mano)
-        cur.wait_event(self.ev_pcl_done)
-        cur.wait_event(self.ev_mano_done)
 
     # ---- algorithmic bytes -----------------------------------------------------
     def mano_bytes_per_hand(self):

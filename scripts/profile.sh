@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r1}
 S=${2:-1024}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --samples $S --no-cpu-baseline --no-e2e --no-overlap"
+CMD="python bench.py --steps 2 --warmup 3 --samples $S --no-cpu-baseline --no-e2e"
 # (1) every launch of the timed steps with its device time (cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/launches_$TAG.log 2>&1
 # (2) one full capture per kernel family (skip the warm-up step launches)
