@@ -31,6 +31,12 @@ SYMBOLS = {
          ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float]
         + [ctypes.c_void_p] * 6 + [ctypes.c_void_p] * 5 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
     ),
+    "hb_mano_head_bwd_reuse": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float]
+        + [ctypes.c_void_p] * 6 + [ctypes.c_void_p] * 5 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
+    ),
     "hb_matrix_to_axis_angle_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "hb_matrix_to_axis_angle_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "hb_rot6d_to_rotmat_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),

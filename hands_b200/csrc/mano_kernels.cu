@@ -948,7 +948,10 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_fo
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   const bool tc = use_tc();
-  float* fh = tc ? ws + ws_tc_base(B, 0) : nullptr;
+  // a backward-sized workspace is laid out as the backward expects it, so hb_mano_head_bwd_reuse() can pick the forward's
+  // feature rows, skinning transforms and v_posed up instead of recomputing them
+  const int lay = workspace_bytes >= hb_mano_workspace_bytes(B, 1) ? 1 : 0;
+  float* fh = tc ? ws + ws_tc_base(B, lay) : nullptr;
   float* fl = tc ? fh + ws_tc_F(B) : nullptr;
   float* vpo = tc ? fl + ws_tc_F(B) : nullptr;
   PoseArgs a{pose, pose_format, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
@@ -971,11 +974,11 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_fo
   return check_launch("mano_skin_fwd_kernel");
 }
 
-extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
-                                const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
-                                const float* g_vertices, const float* g_v3d_cam, const float* g_joints3d, const float* g_j3d_cam,
-                                const float* g_j2d_norm, const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam,
-                                float* g_transl, float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream) {
+static int mano_head_bwd_impl(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
+                              const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
+                              const float* g_vertices, const float* g_v3d_cam, const float* g_joints3d, const float* g_j3d_cam,
+                              const float* g_j2d_norm, const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam,
+                              float* g_transl, float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream, bool reuse) {
   int rc = check_common(h, pose, betas, cam, K, B, workspace, workspace_bytes, 1);
   if (rc) return rc;
   if (B == 0) return 0;
@@ -993,15 +996,19 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_fo
   float* gvl = tc ? gvh + ws_tc_gv(B) : nullptr;
   float* gft = tc ? gvl + ws_tc_gv(B) : nullptr;
   PoseArgs a{pose, pose_format, pre_rot, betas, cam, K, transl, B, img_res, min_s, fh, fl};
-  mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, nullptr, nullptr, nullptr, nullptr);
-  g_launches++;
-  rc = check_launch("mano_pose_fwd_kernel");
-  if (rc) return rc;
+  if (!reuse) {
+    mano_pose_fwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, nullptr, nullptr, nullptr, nullptr);
+    g_launches++;
+    rc = check_launch("mano_pose_fwd_kernel");
+    if (rc) return rc;
+  }
   SkinBwdIn gi{g_vertices, g_v3d_cam, g_joints3d, g_j3d_cam, g_j2d_norm};
   dim3 grid((unsigned)ws_groups(B), NSLICE);
   if (tc) {
-    rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
-    if (rc) return rc;
+    if (!reuse) {
+      rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
+      if (rc) return rc;
+    }
     HB_CUDA(cudaFuncSetAttribute(mano_skin_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinBwdSmemTc));
     mano_skin_bwd_kernel<true><<<grid, VPB, kSkinBwdSmemTc, st>>>(h->c, ws, K, B, img_res, gi, vpo, gvh, gvl);
   } else {
@@ -1019,6 +1026,24 @@ extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_fo
   mano_pose_bwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, o, gft);
   g_launches++;
   return check_launch("mano_pose_bwd_kernel");
+}
+
+extern "C" int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
+                                const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
+                                const float* g_vertices, const float* g_v3d_cam, const float* g_joints3d, const float* g_j3d_cam,
+                                const float* g_j2d_norm, const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam,
+                                float* g_transl, float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream) {
+  return mano_head_bwd_impl(h, pose, pose_format, pre_rot, betas, cam, K, transl, B, img_res, min_s, g_vertices, g_v3d_cam, g_joints3d, g_j3d_cam,
+                            g_j2d_norm, g_cam_t, g_pose, g_betas, g_cam, g_transl, g_pre_rot, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int hb_mano_head_bwd_reuse(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot, const float* betas,
+                                      const float* cam, const float* K, const float* transl, int B, float img_res, float min_s,
+                                      const float* g_vertices, const float* g_v3d_cam, const float* g_joints3d, const float* g_j3d_cam,
+                                      const float* g_j2d_norm, const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam,
+                                      float* g_transl, float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream) {
+  return mano_head_bwd_impl(h, pose, pose_format, pre_rot, betas, cam, K, transl, B, img_res, min_s, g_vertices, g_v3d_cam, g_joints3d, g_j3d_cam,
+                            g_j2d_norm, g_cam_t, g_pose, g_betas, g_cam, g_transl, g_pre_rot, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int hb_rot6d_to_rotmat_fwd(const float* x6, int N, int layout, float* R, void* stream) {

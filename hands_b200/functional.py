@@ -105,7 +105,11 @@ class ManoHeadFunction(torch.autograd.Function):
         j3d = new(B, NOJ, 3) if has_cam and want("j3d.cam") else None
         j2d = new(B, NOJ, 2) if has_cam and want("j2d.norm") else None
         cam_t = new(B, 3) if has_cam and want("cam_t") else None
-        nbytes = lib.hb_mano_workspace_bytes(B, 0)
+        # When a gradient will be asked for, the forward runs in a backward-sized workspace that the backward then picks up
+        # (hb_mano_head_bwd_reuse: no second log-map / Rodrigues / chain / blendshape pass).  Inputs are still what is saved
+        # for autograd's purposes; the workspace is scratch the backward may or may not find (double backward recomputes).
+        keep = any(ctx.needs_input_grad)
+        nbytes = lib.hb_mano_workspace_bytes(B, 1 if keep else 0)
         ws = _workspace(nbytes, dev)
         with torch.cuda.device(dev):
             rc = lib.hb_mano_head_fwd(handle.handle, _ptr(pose), int(is_rotmat), _ptr(pre_rot), _ptr(betas), _ptr(cam), _ptr(K), _ptr(transl),
@@ -113,6 +117,7 @@ class ManoHeadFunction(torch.autograd.Function):
                                       _ptr(cam_t), _ptr(ws), nbytes, _stream())
         _lib.check(rc, "hb_mano_head_fwd")
         ctx.handle, ctx.is_rotmat, ctx.img_res, ctx.min_s = handle, is_rotmat, float(img_res), float(min_s)
+        ctx.ws = ws if keep else None
         ctx.save_for_backward(pose, betas, cam, K, transl, pre_rot)
         ctx.set_materialize_grads(False)
         return vertices, v3d, joints3d, j3d, j2d, cam_t
@@ -130,9 +135,12 @@ class ManoHeadFunction(torch.autograd.Function):
         g_transl = torch.empty_like(transl) if transl is not None else None
         g_pre = torch.empty_like(pre_rot) if pre_rot is not None else None
         nbytes = lib.hb_mano_workspace_bytes(B, 1)
-        ws = _workspace(nbytes, dev)
+        ws, ctx.ws = ctx.ws, None   # used once: a second backward through the same node recomputes
+        bwd = lib.hb_mano_head_bwd_reuse if ws is not None else lib.hb_mano_head_bwd
+        if ws is None:
+            ws = _workspace(nbytes, dev)
         with torch.cuda.device(dev):
-            rc = lib.hb_mano_head_bwd(ctx.handle.handle, _ptr(pose), int(ctx.is_rotmat), _ptr(pre_rot), _ptr(betas), _ptr(cam), _ptr(K),
+            rc = bwd(ctx.handle.handle, _ptr(pose), int(ctx.is_rotmat), _ptr(pre_rot), _ptr(betas), _ptr(cam), _ptr(K),
                                       _ptr(transl), B, ctx.img_res, ctx.min_s, _ptr(g_vertices), _ptr(g_v3d), _ptr(g_joints3d), _ptr(g_j3d),
                                       _ptr(g_j2d), _ptr(g_cam_t), _ptr(g_pose), _ptr(g_betas), _ptr(g_cam), _ptr(g_transl), _ptr(g_pre),
                                       _ptr(ws), nbytes, _stream())

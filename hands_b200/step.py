@@ -81,8 +81,10 @@ class GeometryStep:
                 h["g_cam"] = torch.empty(S, 3, **f32)
                 h["pre_rot"] = torch.empty(S, 3, 3, **f32) if with_pcl else None
                 self.hands.append(h)
+            # one backward-sized workspace per hand side: the backward picks up the forward's intermediates (hb_mano_head_bwd_reuse)
             self.mano_ws_bytes = self.lib.hb_mano_workspace_bytes(S, 1)
-            self.mano_ws = torch.empty((self.mano_ws_bytes + 3) // 4, **f32)
+            self.mano_ws = [torch.empty((self.mano_ws_bytes + 3) // 4, **f32) for _ in range(hands_per_sample)]
+            self.mano_fwd_valid = [False] * hands_per_sample
 
     # ---- pieces (each enqueues on the CURRENT torch stream) ------------------------------------
     def _st(self):
@@ -116,14 +118,17 @@ class GeometryStep:
         h = self.hands[side]
         _lib.check(self.lib.hb_mano_head_fwd(h["handle"].handle, _ptr(h["rotmat"]), 1, _ptr(h["pre_rot"]), _ptr(h["betas"]), _ptr(h["cam"]), _ptr(h["K"]),
                                              None, self.S, float(self.R), 0.1, _ptr(h["vertices"]), _ptr(h["v3d"]), _ptr(h["joints3d"]), _ptr(h["j3d"]),
-                                             _ptr(h["j2d"]), _ptr(h["cam_t"]), _ptr(self.mano_ws), self.mano_ws_bytes, self._st()), "hb_mano_head_fwd")
+                                             _ptr(h["j2d"]), _ptr(h["cam_t"]), _ptr(self.mano_ws[side]), self.mano_ws_bytes, self._st()), "hb_mano_head_fwd")
+        self.mano_fwd_valid[side] = True
 
     def mano_backward(self, side):
         h = self.hands[side]
-        _lib.check(self.lib.hb_mano_head_bwd(h["handle"].handle, _ptr(h["rotmat"]), 1, _ptr(h["pre_rot"]), _ptr(h["betas"]), _ptr(h["cam"]), _ptr(h["K"]),
+        # the backward leaves the forward's part of the workspace intact: it stays valid until the inputs change
+        fn = self.lib.hb_mano_head_bwd_reuse if self.mano_fwd_valid[side] else self.lib.hb_mano_head_bwd
+        _lib.check(fn(h["handle"].handle, _ptr(h["rotmat"]), 1, _ptr(h["pre_rot"]), _ptr(h["betas"]), _ptr(h["cam"]), _ptr(h["K"]),
                                              None, self.S, float(self.R), 0.1, None, _ptr(h["g_v3d"]), None, _ptr(h["g_j3d"]), _ptr(h["g_j2d"]), None,
-                                             _ptr(h["g_rotmat"]), _ptr(h["g_betas"]), _ptr(h["g_cam"]), None, None, _ptr(self.mano_ws),
-                                             self.mano_ws_bytes, self._st()), "hb_mano_head_bwd")
+                      _ptr(h["g_rotmat"]), _ptr(h["g_betas"]), _ptr(h["g_cam"]), None, None, _ptr(self.mano_ws[side]),
+                      self.mano_ws_bytes, self._st()), "hb_mano_head_bwd")
 
     # ---- the fused step ----------------------------------------------------------------------------
     def run(self):

@@ -107,6 +107,17 @@ int hb_mano_head_bwd(const hb_mano* h, const float* pose, int pose_format, const
                      const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam, float* g_transl,
                      float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same backward when `workspace` is the very buffer a preceding hb_mano_head_fwd call on the SAME inputs was given, with
+ * workspace_bytes >= hb_mano_workspace_bytes(B, 1) in both calls and nothing written to it in between: the forward's
+ * feature rows, skinning transforms and v_posed (10.7 KB/hand) are picked up instead of recomputed (two launches and the
+ * blendshape contraction less).  Results are bit-identical to hb_mano_head_bwd. */
+int hb_mano_head_bwd_reuse(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot,
+                           const float* betas, const float* cam, const float* K, const float* transl, int B,
+                           float img_res, float min_s, const float* g_vertices, const float* g_v3d_cam,
+                           const float* g_joints3d, const float* g_j3d_cam, const float* g_j2d_norm,
+                           const float* g_cam_t, float* g_pose, float* g_betas, float* g_cam, float* g_transl,
+                           float* g_pre_rot, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- free functions of the path ------------------------------------------------------------
  * common/rot.py:180-193 matrix_to_axis_angle, forward and backward; N matrices. */
 int hb_matrix_to_axis_angle_fwd(const float* R, int N, float* aa, void* stream);

@@ -759,3 +759,18 @@ def test_pcl_more_than_65535_crops(dev):
     (gs,) = torch.autograd.grad((cs * w[sl]).sum(), xs)
     assert torch.equal(cs, crop[sl]) and torch.equal(gs, gx[sl])
     assert float(crop[-1].abs().max()) > 0
+
+
+def test_backward_reusing_forward_workspace_is_bit_identical(heads, dev):
+    """hb_mano_head_bwd_reuse (the backward picks up the forward's feature rows / transforms / v_posed from the workspace)
+    against hb_mano_head_bwd (everything recomputed): the first backward through a node reuses, the second recomputes."""
+    B = 40
+    rotmat, betas, cam, K = [t.to(dev) for t in synthetic_head_inputs(B, seed=21, small_s_frac=0.2)]
+    r, b, c = rotmat.clone().requires_grad_(True), betas.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+    o = heads[True](r, b, c, K)
+    g = torch.Generator(device=dev).manual_seed(0)
+    loss = (o["v3d.cam.r"] * torch.randn(B, 778, 3, generator=g, device=dev)).sum() + (o["j2d.norm.r"] * torch.randn(B, 21, 2, generator=g, device=dev)).sum()
+    first = torch.autograd.grad(loss, (r, b, c), retain_graph=True)
+    second = torch.autograd.grad(loss, (r, b, c))
+    for a, bb in zip(first, second):
+        assert torch.equal(a, bb)
