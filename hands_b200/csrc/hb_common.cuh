@@ -66,6 +66,8 @@ __host__ __device__ inline float tf32_round(float x) {
 
 size_t tc_smem_bytes();
 int launch_blend_tc(const float* Fhi, const float* Flo, const float* Bhi, const float* Blo, const float* vt, int B, float* vp, cudaStream_t st);
+constexpr int G_MAXSPLIT = 4;   // split-K parts of the backward feature contraction (partials [part][B128][160] in the workspace)
+int gfeat_nsplit(int B);
 int launch_gfeat_tc(const float* gvh, const float* gvl, const float* Ph, const float* Pl, int B, float* gF, cudaStream_t st);
 extern int g_mano_tc;   // 1: blendshape contraction on tcgen05 (mano_tc.cu); 0: register-tiled FFMA
 

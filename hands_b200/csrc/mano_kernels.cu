@@ -38,7 +38,7 @@ __host__ __device__ inline size_t ws_tc_vp(int B) { return ws_g128(B) * 128 * 24
 // backward only: dL/dv_posed slabs hi/lo [G128][300][1024] and the reduced feature gradient [G128*128][160]
 __host__ __device__ inline size_t ws_tc_gv(int B) { return ws_g128(B) * 300 * 1024; }
 __host__ __device__ inline size_t ws_tc_end(int B, int backward) {
-  return ws_tc_base(B, backward) + 2 * ws_tc_F(B) + ws_tc_vp(B) + (backward ? 2 * ws_tc_gv(B) + ws_g128(B) * 128 * 160 : 0);
+  return ws_tc_base(B, backward) + 2 * ws_tc_F(B) + ws_tc_vp(B) + (backward ? 2 * ws_tc_gv(B) + (size_t)G_MAXSPLIT * ws_g128(B) * 128 * 160 : 0);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -580,8 +580,8 @@ struct PoseBwdArgs {
   float* g_pose; float* g_betas; float* g_cam; float* g_transl; float* g_pre_rot;
 };
 
-__global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArgs a, const float* __restrict__ ws, PoseBwdArgs o,
-                                                            const float* __restrict__ gFt) {
+__global__ void __launch_bounds__(128, 4) mano_pose_bwd_kernel(ManoConst c, PoseArgs a, const float* __restrict__ ws, PoseBwdArgs o,
+                                                            const float* __restrict__ gFt, int gf_parts, size_t gf_stride) {
   const int i = threadIdx.x & 15;
   const int braw = blockIdx.x * 8 + (threadIdx.x >> 4);
   const bool live = braw < a.B;
@@ -621,14 +621,16 @@ __global__ void __launch_bounds__(128) mano_pose_bwd_kernel(ManoConst c, PoseArg
       for (int k = 0; k < 6; ++k) gO[k] += po[k];
     }
   }
-  if (gFt) {   // feature gradient reduced over all vertices by the tensor-core kernel: [hand][160]
-    const float* pf = gFt + (size_t)b * 160;
-    if (i > 0) {
+  if (gFt) {   // feature gradient reduced over all vertices by the tensor-core kernel: split-K partials [part][hand][160], added in order
+    for (int part = 0; part < gf_parts; ++part) {
+      const float* pf = gFt + (size_t)part * gf_stride + (size_t)b * 160;
+      if (i > 0) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) gFr[k] = __ldg(pf + (i - 1) * 9 + k);
-    } else {
+        for (int k = 0; k < 9; ++k) gFr[k] += __ldg(pf + (i - 1) * 9 + k);
+      } else {
 #pragma unroll
-      for (int l = 0; l < NB; ++l) gbeta[l] = __ldg(pf + NPF + l);
+        for (int l = 0; l < NB; ++l) gbeta[l] += __ldg(pf + NPF + l);
+      }
     }
   }
   // gradient arriving at this posed joint: joints3d = t + t1 ; j3d_cam = joints3d + cam_t ; j2d = proj(j3d_cam)
@@ -1023,7 +1025,7 @@ static int mano_head_bwd_impl(const hb_mano* h, const float* pose, int pose_form
     if (rc) return rc;
   }
   PoseBwdArgs o{g_joints3d, g_j3d_cam, g_j2d_norm, g_cam_t, g_pose, g_betas, g_cam, g_transl, g_pre_rot};
-  mano_pose_bwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, o, gft);
+  mano_pose_bwd_kernel<<<(B + 7) / 8, 128, 0, st>>>(h->c, a, ws, o, gft, tc ? gfeat_nsplit(B) : 0, (size_t)ws_g128(B) * 128 * 160);
   g_launches++;
   return check_launch("mano_pose_bwd_kernel");
 }

@@ -242,7 +242,7 @@ __device__ __forceinline__ void umma_tf32_g(uint32_t d_tmem, uint64_t adesc, uin
 
 __global__ void __launch_bounds__(TC_THREADS, 1) mano_gfeat_tc_kernel(const float* __restrict__ gvh, const float* __restrict__ gvl,
                                                                        const float* __restrict__ Ph, const float* __restrict__ Pl,
-                                                                       int B, float* __restrict__ gF) {
+                                                                       int B, int nsplit, float* __restrict__ gF) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GSmem::BARS);
   uint64_t* full = bars;
@@ -264,7 +264,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mano_gfeat_tc_kernel(const floa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr int NFILL = G_KSTEPS / G_KC;
+  // split-K: part blockIdx.y of nsplit takes a contiguous range of the 75 ring fills (>= 3 fills each, so every one of the
+  // three accumulators is initialised) and writes its own partial gF[part][B][160]; the pose backward adds them in order
+  constexpr int NFILL_ALL = G_KSTEPS / G_KC;
+  const int part = blockIdx.y;
+  const int f0 = part * NFILL_ALL / nsplit, f1 = (part + 1) * NFILL_ALL / nsplit;
+  const int NFILL = f1 - f0;
+  gF += (size_t)part * (size_t)((B + TC_M - 1) / TC_M) * TC_M * G_N;
   constexpr uint32_t A_BYTES = G_KC * G_A_SLAB * 4, B_BYTES = G_KC * G_B_SLAB * 4;
 
   if (warp == 0) {
@@ -276,10 +282,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mano_gfeat_tc_kernel(const floa
         mbar_wait(&empty[s], (n & 1) ^ 1);
         uint8_t* st = smem + s * GSmem::STAGE;
         mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
-        bulk_g2s(st, ah + (size_t)f * G_KC * G_A_SLAB, A_BYTES, &full[s]);
-        bulk_g2s(st + A_BYTES, al + (size_t)f * G_KC * G_A_SLAB, A_BYTES, &full[s]);
-        bulk_g2s(st + 2 * A_BYTES, Ph + (size_t)f * G_KC * G_B_SLAB, B_BYTES, &full[s]);
-        bulk_g2s(st + 2 * A_BYTES + B_BYTES, Pl + (size_t)f * G_KC * G_B_SLAB, B_BYTES, &full[s]);
+        bulk_g2s(st, ah + (size_t)(f0 + f) * G_KC * G_A_SLAB, A_BYTES, &full[s]);
+        bulk_g2s(st + A_BYTES, al + (size_t)(f0 + f) * G_KC * G_A_SLAB, A_BYTES, &full[s]);
+        bulk_g2s(st + 2 * A_BYTES, Ph + (size_t)(f0 + f) * G_KC * G_B_SLAB, B_BYTES, &full[s]);
+        bulk_g2s(st + 2 * A_BYTES + B_BYTES, Pl + (size_t)(f0 + f) * G_KC * G_B_SLAB, B_BYTES, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -339,10 +345,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mano_gfeat_tc_kernel(const floa
   }
 }
 
+int gfeat_nsplit(int B) {
+  // K (2400 vertex coordinates) is always split over G_MAXSPLIT CTAs: one CTA per 128 hands left SMs idle below 19k hands
+  // (64 of 148 at B = 8192, 8 at B = 1024).  The count does not depend on B, so a hand's gradient is the same sum in the same
+  // order however the batch is sharded.
+  (void)B;
+  return G_MAXSPLIT;
+}
+
 int launch_gfeat_tc(const float* gvh, const float* gvl, const float* Ph, const float* Pl, int B, float* gF, cudaStream_t st) {
   const int groups = (B + TC_M - 1) / TC_M;
+  const int nsplit = gfeat_nsplit(B);
   HB_CUDA(cudaFuncSetAttribute(mano_gfeat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSmem::TOTAL));
-  mano_gfeat_tc_kernel<<<groups, TC_THREADS, GSmem::TOTAL, st>>>(gvh, gvl, Ph, Pl, B, gF);
+  mano_gfeat_tc_kernel<<<dim3(groups, nsplit), TC_THREADS, GSmem::TOTAL, st>>>(gvh, gvl, Ph, Pl, B, nsplit, gF);
   g_launches++;
   return check_launch("mano_gfeat_tc_kernel");
 }
