@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(PCL_THREADS) pcl_fwd_kernel(const float* __res
   __shared__ int reg[5];                          // staged source region: x0, y0, ncols, nrows, staged?
   __shared__ float4 rowrec[PCL_TR];               // per output row of the tile: ly0, ly1, offsets of its two source rows
   __shared__ uint64_t src_bar;
-  const int q = blockIdx.x;   // crops on grid.x (no 65,535 limit); row band on grid.y
+  const int q = blockIdx.y;   // (launches are split at 65,535 crops by the host)
   const Crop c = load_crop(params + (size_t)q * PF);
   const int s = c.s;
-  const int Y0 = blockIdx.y * PCL_TR;
+  const int Y0 = blockIdx.x * PCL_TR;
   const int Y1 = min(Y0 + PCL_TR, R) - 1;
   const float* src = img + (size_t)(q / crops_per_img) * C * R * R;
   float* dst = out + (size_t)q * C * R * R;
@@ -441,14 +441,15 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
   __shared__ float tu[RT ? PCL_XB + 8 : 1];   // linspace(0,1,s) of the CTA's intermediate columns (compile-time resolution only)
   __shared__ float tv[RT ? PCL_TV : 1];       // ... and of the band's intermediate rows
   __shared__ __align__(16) float2 coltab[RT ? PCL_XB : 1];   // per output column: (weight of the upper tap, lower tap byte offset in a band row)
-  const int q = blockIdx.x;   // crops on grid.x (no 65,535 limit); (row segment, column block) on grid.y
+  const int q = blockIdx.y;   // band index on grid.x (fastest): the CTAs of one crop are adjacent in launch order -- measured 401 vs 420 us
+                              // per 2048 crops against crops on grid.x; launches are split at 65,535 crops by the host
   const Crop c = load_crop(params + (size_t)q * PF);
   const int s = c.s;
   // CTA = (crop, row segment, block of output columns).  The column split halves the intermediate band and its source
   // footprint (band + staged tile fit the shared-memory budget of 5 CTAs/SM for every box up to the image size); walking
   // the segment's bands in one CTA pays the per-crop set-up once and lets the next band's tile fly during the resize.
   const int nxb = RT ? RT / PCL_XB : nxb_arg;
-  const int yseg = RT ? (int)(blockIdx.y / (RT / PCL_XB)) : (int)blockIdx.y / nxb, xb = blockIdx.y - yseg * nxb;
+  const int yseg = RT ? (int)(blockIdx.x / (RT / PCL_XB)) : (int)blockIdx.x / nxb, xb = blockIdx.x - yseg * nxb;
   const int xbw = RT ? PCL_XB : (((R + nxb - 1) / nxb + 1) & ~1);
   const int segrows = RT ? ((RT / PCL_NSEG + PCL_TR - 1) / PCL_TR) * PCL_TR : (((R + PCL_NSEG - 1) / PCL_NSEG + PCL_TR - 1) / PCL_TR) * PCL_TR;
   const int X0 = xb * xbw, X1 = min(X0 + xbw, R) - 1;
@@ -840,9 +841,13 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
   extern __shared__ __align__(16) float sm[];
   const int q = q_base + blockIdx.y;
   const float* rec = params + (size_t)q * PF;
+  const int j0 = blockIdx.x * PCL_JR;
+  {
+    const int s_only = __float_as_int(__ldg(rec + 18));   // one load decides whether this band exists
+    if (j0 >= s_only || s_only > (RT ? RT : R_arg)) return;
+  }
   const Crop c = load_crop(rec);
   const int s = c.s;
-  const int j0 = blockIdx.x * PCL_JR;
   if (j0 >= s || s > R) return;   // s > R is outside the supported domain of the backward (workspace sized for s <= R)
   const int j1 = min(j0 + PCL_JR, s) - 1;
   float* tl1 = sm;                                   // [R]
@@ -973,9 +978,13 @@ __global__ void __launch_bounds__(PCL_M4T, 3) pcl_bwd_mid4_kernel(const float* _
   extern __shared__ __align__(16) float sm[];
   const int q = q_base + blockIdx.y;
   const float* rec = params + (size_t)q * PF;
+  const int j0 = blockIdx.x * PCL_JR;
+  {
+    const int s_only = __float_as_int(__ldg(rec + 18));   // one load decides whether this band exists
+    if (j0 >= s_only || s_only > (RT ? RT : R_arg)) return;
+  }
   const Crop c = load_crop(rec);
   const int s = c.s;
-  const int j0 = blockIdx.x * PCL_JR;
   if (j0 >= s || s > R) return;
   const int j1 = min(j0 + PCL_JR, s) - 1;
   const int nx4 = R >> 2;
@@ -1361,26 +1370,37 @@ static int launch_fwd(const SrcT* img, const float* params, int n_crops, int cro
   static int want_tma = -1;
   if (want_tma < 0) { const char* e = getenv("HB_PCL_TMA"); want_tma = (e && e[0] == '0') ? 0 : 1; }
   const int tma_ok = want_tma && (R % (U8 ? 16 : 4) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
-  dim3 grid(n_crops, (R + PCL_TR - 1) / PCL_TR);
   const int nxb = (R == 224) ? 224 / PCL_XB : (R > 128 ? 2 : 1);   // column blocks of the fast kernel
   const unsigned cpi_mul = (unsigned)((0x100000000ull + (unsigned)crops_per_img - 1) / (unsigned)crops_per_img);   // q / cpi == umulhi(q, cpi_mul) for q * cpi < 2^32
-  if constexpr (!U8) {
-    if (pcl_exact()) {
-      auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
-      HB_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      fwd_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, R, out, PCL_TR + 2, (int)smem, tma_ok);
-      g_launches++;
-      return check_launch("pcl_fwd_kernel");
-    }
-  }
   const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
-  auto fast_kernel = (R == 224 && v2) ? pcl_fwd_fast_kernel<C, 224, SrcT, true> : (v2 ? pcl_fwd_fast_kernel<C, 0, SrcT, true> : pcl_fwd_fast_kernel<C, 0, SrcT, false>);
-  HB_CUDA(cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (crops_per_img > 1 && (unsigned long long)n_crops * (unsigned)crops_per_img >= 0x100000000ull) { set_error("hb_pcl_fwd: n_crops * crops_per_img must be below 2^32"); return HB_E_ARG; }
-  grid.y = PCL_NSEG * nxb;
-  fast_kernel<<<grid, PCL_THREADS, smem, st>>>(img, params, crops_per_img, crops_per_img == 1 ? 0u : cpi_mul, R, out, (int)smem, tma_ok, nxb, nrm);
-  g_launches++;
-  return check_launch("pcl_fwd_fast_kernel");
+  const size_t plane = (size_t)C * R * R;
+  // crops sit on grid.y (limit 65,535): larger batches go out as several launches, split at a multiple of crops_per_img
+  const int max_chunk = (65535 / crops_per_img) * crops_per_img;
+  if (max_chunk <= 0) { set_error("hb_pcl_fwd: crops_per_img too large"); return HB_E_ARG; }
+  for (int base = 0; base < n_crops; base += max_chunk) {
+    const int nc = n_crops - base < max_chunk ? n_crops - base : max_chunk;
+    const SrcT* img_c = img + (size_t)(base / crops_per_img) * plane;
+    const float* par_c = params + (size_t)base * PF;
+    float* out_c = out + (size_t)base * plane;
+    if constexpr (!U8) {
+      if (pcl_exact()) {
+        auto fwd_kernel = (R == 224) ? pcl_fwd_kernel<C, 224> : pcl_fwd_kernel<C, 0>;
+        HB_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fwd_kernel<<<dim3((R + PCL_TR - 1) / PCL_TR, nc), PCL_THREADS, smem, st>>>(img_c, par_c, crops_per_img, R, out_c, PCL_TR + 2, (int)smem, tma_ok);
+        g_launches++;
+        const int rc = check_launch("pcl_fwd_kernel");
+        if (rc) return rc;
+        continue;
+      }
+    }
+    auto fast_kernel = (R == 224 && v2) ? pcl_fwd_fast_kernel<C, 224, SrcT, true> : (v2 ? pcl_fwd_fast_kernel<C, 0, SrcT, true> : pcl_fwd_fast_kernel<C, 0, SrcT, false>);
+    HB_CUDA(cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fast_kernel<<<dim3(PCL_NSEG * nxb, nc), PCL_THREADS, smem, st>>>(img_c, par_c, crops_per_img, crops_per_img == 1 ? 0u : cpi_mul, R, out_c, (int)smem, tma_ok, nxb, nrm);
+    g_launches++;
+    const int rc = check_launch("pcl_fwd_fast_kernel");
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 template <typename SrcT>
