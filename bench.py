@@ -269,10 +269,11 @@ def run_ours(args, rank, world, local_rank):
                           "frac": ab[name] / tt[name] / 1e9 / peak, "traffic": next((v for k, v in traffic.items() if k.startswith(name[:-len("_kernel")])), None),
                           "crops_per_launch": ks.n}
         del ks
-        try:
-            tf32_peak = L.measure_tf32_peak(dev)
-        except Exception:
-            tf32_peak = None
+        if not args.quick:   # (kept out of the profiling command's launch list)
+            try:
+                tf32_peak = L.measure_tf32_peak(dev)
+            except Exception:
+                tf32_peak = None
 
     # ---- e2e: host buffers, copies inside the timed region ---------------------------------------------
     e2e = e2e_f32 = None

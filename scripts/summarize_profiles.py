@@ -39,7 +39,7 @@ def launches():
             pass
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(OUT, f"launches_{TAG}.txt"), "w") as fh:
-        fh.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (bench.py --steps 2 --warmup 3 --no-overlap; all launches incl. warm-up)\n")
+        fh.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (bench.py --steps 2 --warmup 3 --samples 1024 --quick --no-e2e --no-cpu-baseline; all launches incl. warm-up and the per-kernel timing legs)\n")
         fh.write(f"# per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  total {total/1e6:.3f} ms\n")
         fh.write(f"{'kernel':80s} {'launches':>8s} {'mean_us':>10s} {'total_ms':>10s} {'share':>7s}\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
