@@ -1125,43 +1125,6 @@ constexpr int PCL_REG = 1536;           // region pixels staged in shared memory
 // g_img is written once per pixel: no float atomics, no memset.
 constexpr int PCL_RECS = 4;            // crop records cached in shared memory per image
 
-// Region of a crop's intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31] of a source tile:
-// sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5); the pre-image of that box
-// under the inverse homography is a convex quad, bounded by the box of its four corners.  bx = {i0, i1, j0, j1}, empty
-// (i0 > i1) when the crop cannot reach the tile or lies outside the supported domain of the backward (s > R).
-__device__ __forceinline__ void pcl_region_box(const float* rec, int tx0, int ty0, int R, int* bx) {
-  const int s = __float_as_int(rec[18]);
-  bx[0] = 1; bx[1] = 0; bx[2] = 1; bx[3] = 0;
-  // cheap cull: the crop's footprint box (from the setup kernel) against this tile
-  if (s > R || __float_as_int(rec[22]) > tx0 + PCL_TS || __float_as_int(rec[23]) < tx0 - 1 ||
-      __float_as_int(rec[24]) > ty0 + PCL_TS || __float_as_int(rec[25]) < ty0 - 1) return;
-  float Pi[9];
-#pragma unroll
-  for (int e = 0; e < 9; ++e) Pi[e] = rec[9 + e];
-  const float sm1 = (float)(s - 1);
-  float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
-  bool bad = false;
-#pragma unroll
-  for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-    for (int cx = 0; cx < 2; ++cx) {
-      const float gx = (float)tx0 - 0.5f + 33.0f * cx, gy = (float)ty0 - 0.5f + 33.0f * cy;
-      const float U = Pi[0] * gx + Pi[1] * gy + Pi[2];
-      const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
-      const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
-      if (Wd > 1e-12f) {
-        const float iw = __frcp_rn(Wd);
-        const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
-        ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
-      } else bad = true;
-    }
-  if (bad) { bx[0] = 0; bx[1] = s - 1; bx[2] = 0; bx[3] = s - 1; }
-  else {
-    bx[0] = max(0, (int)floorf(ilo - 0.25f)); bx[1] = min(s - 1, (int)ceilf(ihi + 0.25f));
-    bx[2] = max(0, (int)floorf(jlo - 0.25f)); bx[3] = min(s - 1, (int)ceilf(jhi + 0.25f));
-  }
-}
-
 template <int C, int RT>
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img) {
@@ -1174,7 +1137,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   float* tu = reinterpret_cast<float*>(img_sm + PCL_REG * 24 + PCL_CNT_BYTES + PCL_LST_BYTES);             // [64] linspace of the region's columns
   float* tv = tu + 64;                                                                                              // [64] ... and rows
   __shared__ int overflow;
-  __shared__ int boxes[PCL_RECS][4];
+  __shared__ int box[4];
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
   const int im = img_base + blockIdx.y;
@@ -1185,39 +1148,63 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) acc[r][ch] = 0.f;
   // the records of the image's (first PCL_RECS) crops are fetched once, all fields in flight together, instead of a chain
-  // of dependent global loads per crop; then warp k works out the region box of crop k, all crops at once, so the per-crop
-  // loop below has no single-warp section (and a crop that cannot reach the tile costs no barrier at all)
+  // of dependent global loads per crop
   __shared__ float recs[PCL_RECS * PF];
   for (int e = threadIdx.x; e < min(crops_per_img, PCL_RECS) * PF; e += PCL_THREADS) recs[e] = __ldg(params + (size_t)im * crops_per_img * PF + e);
-  __syncthreads();
-  if (lyb < min(crops_per_img, PCL_RECS)) {
-    int bx[4];
-    pcl_region_box(recs + lyb * PF, tx0, ty0, R, bx);
-    if (lx < 4) boxes[lyb][lx] = lx == 0 ? bx[0] : (lx == 1 ? bx[1] : (lx == 2 ? bx[2] : bx[3]));
-  }
   __syncthreads();
   for (int k = 0; k < crops_per_img; ++k) {
     if (k >= PCL_RECS) {   // more crops per image than cached records: fetch this one into slot 0 (block-uniform)
       __syncthreads();
       if (threadIdx.x < PF) recs[threadIdx.x] = __ldg(params + (size_t)(im * crops_per_img + k) * PF + threadIdx.x);
       __syncthreads();
-      if (threadIdx.x < 32) {
-        int bx[4];
-        pcl_region_box(recs, tx0, ty0, R, bx);
-        if (lx < 4) boxes[0][lx] = lx == 0 ? bx[0] : (lx == 1 ? bx[1] : (lx == 2 ? bx[2] : bx[3]));
-      }
-      __syncthreads();
     }
-    const int slot = k < PCL_RECS ? k : 0;
-    const float* rec = recs + slot * PF;   // always shared memory
-    const int ri0 = boxes[slot][0], ri1 = boxes[slot][1], rj0 = boxes[slot][2], rj1 = boxes[slot][3];
-    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
+    const float* rec = recs + (k < PCL_RECS ? k : 0) * PF;   // always shared memory
+    // cheap cull: the crop's footprint box (from the setup kernel) against this tile
+    if (__float_as_int(*(rec + 22)) > tx0 + PCL_TS || __float_as_int(*(rec + 23)) < tx0 - 1 ||
+        __float_as_int(*(rec + 24)) > ty0 + PCL_TS || __float_as_int(*(rec + 25)) < ty0 - 1) continue;
     const int s = __float_as_int(*(rec + 18));
+    if (s > R) continue;   // outside the supported domain of the backward (see hb_pcl_bwd in the header)
     const float* base = ws + __float_as_int(*(rec + 21));
     const float4* G = reinterpret_cast<const float4*>(base);
-    __syncthreads();  // previous crop's readers are done with cnt/lst/ent and the tables
-    for (int idx = threadIdx.x; idx < (PCL_CELLS * PCL_CELLS + 3) / 4; idx += PCL_THREADS) reinterpret_cast<int4*>(cnt)[idx] = make_int4(0, 0, 0, 0);
-    if (threadIdx.x == 0) overflow = 0;
+    __syncthreads();  // previous crop's readers are done with cnt/lst/ent and the region box
+    if (threadIdx.x < 32) {
+      // 1. (warp 0) region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
+      //    sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5); the pre-image
+      //    of that box under the inverse homography is a convex quad, bounded by the box of its four corners
+      float Pi[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Pi[e] = *(rec + 9 + e);
+      const float sm1 = (float)(s - 1);
+      float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
+      bool bad = false;
+#pragma unroll
+      for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          const float gx = (float)tx0 - 0.5f + 33.0f * cx, gy = (float)ty0 - 0.5f + 33.0f * cy;
+          const float U = Pi[0] * gx + Pi[1] * gy + Pi[2];
+          const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
+          const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
+          if (Wd > 1e-12f) {
+            const float iw = __frcp_rn(Wd);
+            const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
+            ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
+          } else bad = true;
+        }
+      if (threadIdx.x == 0) {
+        if (bad) { box[0] = 0; box[1] = s - 1; box[2] = 0; box[3] = s - 1; }
+        else {
+          box[0] = max(0, (int)floorf(ilo - 0.25f)); box[1] = min(s - 1, (int)ceilf(ihi + 0.25f));
+          box[2] = max(0, (int)floorf(jlo - 0.25f)); box[3] = min(s - 1, (int)ceilf(jhi + 0.25f));
+        }
+        overflow = 0;
+      }
+    } else {
+      for (int idx = threadIdx.x - 32; idx < (PCL_CELLS * PCL_CELLS + 3) / 4; idx += PCL_THREADS - 32) reinterpret_cast<int4*>(cnt)[idx] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const int ri0 = box[0], ri1 = box[1], rj0 = box[2], rj1 = box[3];
+    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
     const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
     const Crop c = load_crop_any(rec);
     float P[9];
