@@ -700,10 +700,11 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
             if (o1r != cur1) { hrow(o1r, h1); cur1 = o1r; }
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-              const float oa = fmaf(rr.y, h1[0][ch], __fmul_rn(rr.x, h0[0][ch]));
-              const float ob = fmaf(rr.y, h1[1][ch], __fmul_rn(rr.x, h0[1][ch]));
-              if (V2) __stcs(reinterpret_cast<float2*>(op + ch * plane), make_float2(oa, ob));
-              else { __stcs(op + ch * plane, oa); if (two) __stcs(op + ch * plane + 1, ob); }
+              // both columns in one packed multiply + one packed FMA (bit-identical lanes)
+              const float2 o2 = __ffma2_rn(make_float2(rr.y, rr.y), make_float2(h1[0][ch], h1[1][ch]),
+                                           __fmul2_rn(make_float2(rr.x, rr.x), make_float2(h0[0][ch], h0[1][ch])));
+              if (V2) __stcs(reinterpret_cast<float2*>(op + ch * plane), o2);
+              else { __stcs(op + ch * plane, o2.x); if (two) __stcs(op + ch * plane + 1, o2.y); }
             }
           }
         }
@@ -1047,10 +1048,13 @@ __global__ void __launch_bounds__(PCL_M4T, 3) pcl_bwd_mid4_kernel(const float* _
               while (i0 > jc) { finish_row(jc); ++jc; }   // group-uniform (groups are whole warps)
 #pragma unroll
               for (int ch = 0; ch < C; ++ch) {
-                cur[ch].x = fmaf(T.x, gv[u][ch].x, cur[ch].x); cur[ch].y = fmaf(T.x, gv[u][ch].y, cur[ch].y);
-                cur[ch].z = fmaf(T.x, gv[u][ch].z, cur[ch].z); cur[ch].w = fmaf(T.x, gv[u][ch].w, cur[ch].w);
-                nxt[ch].x = fmaf(T.y, gv[u][ch].x, nxt[ch].x); nxt[ch].y = fmaf(T.y, gv[u][ch].y, nxt[ch].y);
-                nxt[ch].z = fmaf(T.y, gv[u][ch].z, nxt[ch].z); nxt[ch].w = fmaf(T.y, gv[u][ch].w, nxt[ch].w);
+                // packed f32x2 FMAs (SASS FFMA2): each lane is the same IEEE fmaf as the scalar form, half the issue slots
+                const float2 w0 = make_float2(T.x, T.x), w1 = make_float2(T.y, T.y);
+                const float2 glo = make_float2(gv[u][ch].x, gv[u][ch].y), ghi = make_float2(gv[u][ch].z, gv[u][ch].w);
+                const float2 c0 = __ffma2_rn(w0, glo, make_float2(cur[ch].x, cur[ch].y)), c1 = __ffma2_rn(w0, ghi, make_float2(cur[ch].z, cur[ch].w));
+                const float2 n0 = __ffma2_rn(w1, glo, make_float2(nxt[ch].x, nxt[ch].y)), n1 = __ffma2_rn(w1, ghi, make_float2(nxt[ch].z, nxt[ch].w));
+                cur[ch] = make_float4(c0.x, c0.y, c1.x, c1.y);
+                nxt[ch] = make_float4(n0.x, n0.y, n1.x, n1.y);
               }
             }
           }
