@@ -110,3 +110,32 @@ def test_xdict_contract():
     assert sorted(d.keys()) == ["a", "b"]
     with pytest.raises(AssertionError):
         d.merge(e)
+
+
+def test_stale_binary_detection_uses_source_digest(monkeypatch):
+    """_lib.load() rebuilds when the sha256 of csrc/ + the header + the flags differs from the stamp written at build time
+    (mtimes do not survive the copy to a GPU box; content does), and refuses a binary whose hb_version() is not the header's."""
+    from hands_b200 import _build, _lib
+
+    _build.build()
+    assert not _build.needs_build()
+    monkeypatch.setattr(_build, "NVCC_FLAGS", _build.NVCC_FLAGS + ["-DHB_SOMETHING_ELSE"])
+    assert _build.needs_build()
+    monkeypatch.undo()
+    assert not _build.needs_build()
+    assert _lib.load().hb_version() == _build.header_version() == 200
+
+
+def test_cpu_baseline_legs_run():
+    """The CPU legs bench.py reports (scripts/bench_legs.py) stay runnable: per-sample loop, 1 thread, batched fixed-s."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from scripts import bench_legs as L
+
+    v, dt = L.cpu_loop_all_threads(2, 1, 0)
+    v1, _ = L.cpu_loop_one_thread(2)
+    vb, _ = L.cpu_batched(2, 1, 0)
+    assert v > 0 and v1 > 0 and vb > 0 and dt > 0
+    c1 = L.config_c1()
+    assert c1["hands_per_s"] > 0
