@@ -89,7 +89,9 @@ size_t hb_mano_workspace_bytes(int B, int backward);
  *             (src/models/hands_light/model.py:330-334, the PCL orientation fix-up)
  *   betas (B,10)   cam (B,3)=[s,tx,ty] or NULL   K (B,3,3) or NULL   transl (B,3) or NULL
  * Outputs (each or NULL): vertices (B,778,3), v3d_cam (B,778,3), joints3d (B,21,3),
- *   j3d_cam (B,21,3), j2d_norm (B,21,2), cam_t (B,3).  Camera outputs need cam and K. */
+ *   j3d_cam (B,21,3), j2d_norm (B,21,2), cam_t (B,3).  Camera outputs need cam and K.
+ * Workspace: >= hb_mano_workspace_bytes(B, 0).  Given >= hb_mano_workspace_bytes(B, 1) bytes the forward lays its
+ *   intermediates out as the backward expects them, which is what hb_mano_head_bwd_reuse() relies on. */
 int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_format, const float* pre_rot,
                      const float* betas, const float* cam, const float* K, const float* transl, int B,
                      float img_res, float min_s, float* vertices, float* v3d_cam, float* joints3d,
