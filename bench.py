@@ -507,8 +507,8 @@ def run_e2e(step, args, dev, world, barrier, src_u8=True, steps=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=8192, help="samples per GPU per step (C4: 65536 / 8)")
     ap.add_argument("--ref-samples", type=int, default=256, help="samples per CPU-reference step (bounded sample)")
