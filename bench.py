@@ -211,8 +211,15 @@ def run_ours(args, rank, world, local_rank):
     step = GeometryStep(S, dev, img_res=IMG_RES, seed=rank)
     metrics_vec = torch.zeros(64, device=dev)
 
+    graph_launches = 0
+    if not args.no_graph:
+        graph_launches = step.capture()       # the 33 launches of a step replayed from one CUDA graph
+
     def one_step():
-        step.run()
+        if graph_launches:
+            step.replay()
+        else:
+            step.run()
         if world > 1:
             dist.all_reduce(metrics_vec)   # packed metric scalars (north_star); no data-path collective
 
@@ -235,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
         one_step()
     e1.record()
     barrier()
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() - l0 + graph_launches * args.steps   # replays launch the captured kernels without host calls
     elapsed = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -347,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
                    "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
-                   "streams": "single",
+                   "streams": "single", "cuda_graph": bool(graph_launches),
                    "pcl_forward": "exact (torch op order)" if os.environ.get("HB_PCL_EXACT", "0") == "1" else "default (reference sample positions, separable resize)",
                    "mano_contractions": "tcgen05 3xTF32" if os.environ.get("HB_MANO_TC", "1") != "0" else "ffma"},
         "clocks": clocks,
@@ -515,6 +522,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=1024, help="samples per pipelined e2e chunk")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--quick", action="store_true", help="skip the side legs (other configs, fp32-source e2e, CPU worker pool)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
