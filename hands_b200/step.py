@@ -165,7 +165,8 @@ class GeometryStep:
         torch.cuda.synchronize(self.dev)
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):
+        # thread_local: other threads of the process (NCCL's watchdog under torchrun) keep making CUDA calls during the capture
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
             self.run()
         self.launches_per_replay = _lib.launch_count() - n0
         return self.launches_per_replay
