@@ -345,6 +345,16 @@ def run_ours(args, rank, world, local_rank):
     bps = bytes_per_sample
     step_bytes = bps * S
     step_gbs = value / world / HANDS_PER_SAMPLE * bps / 1e9
+    # DRAM traffic of one step, from the committed per-launch ncu captures (1024-image launches) scaled to this step's
+    # launches; MANO kernels from the same capture file (8192-hand launches would be ~8x the 1024-hand figures)
+    step_traffic = None
+    try:
+        per1024 = sum(kern[k]["traffic"] for k in kern)
+        mano_names = ("mano_pose_fwd_kernel", "mano_blend_tc_kernel", "mano_skin_fwd_kernel", "mano_skin_bwd_kernel", "mano_gfeat_tc_kernel", "mano_pose_bwd_kernel")
+        mano1024 = sum(traffic.get(k, 0.0) for k in mano_names)
+        step_traffic = (per1024 + HANDS_PER_SAMPLE * mano1024) * (S / 1024.0)
+    except Exception:
+        pass
     mano_hps = 2 * S / ((fam["mano_fwd r+l (pose + blend_tc + skin)"]["ms"] + fam["mano_bwd r+l (pose + blend_tc + skin + gfeat_tc + pose)"]["ms"]) * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -363,10 +373,11 @@ def run_ours(args, rank, world, local_rank):
         "e2e": e2e,
         "e2e_fp32_source": e2e_f32,
         "roofline": {"bound": "hbm", "kernel": "fused C4 step (all kernels of one fwd+bwd pass)", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": step_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": step_gbs / peak, "traffic": step_traffic, "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of the whole step (SURVEY.md 8(d): %.0f B/sample) / device time of the timed region; "
-                             "per-kernel fractions (each kernel timed alone, one launch over %d crops) are under `kernels`, dram traffic per launch "
-                             "from %s" % (bps, kern[dom]["crops_per_launch"], traffic_src),
+                             "per-kernel fractions (each kernel timed alone, one launch over %d crops) are under `kernels`; `traffic` = dram bytes "
+                             "of one step = the per-launch `ncu --set full` captures of %s scaled to this step's launches (vs %.1f GB algorithmic)"
+                             % (bps, kern[dom]["crops_per_launch"], traffic_src, bps * S / 1e9),
                      "alg_bytes_per_sample": bps,
                      "tensor_peak_tf32_tflops": tf32_peak, "tensor_peak_source": "measured here: torch.matmul fp32 with allow_tf32, 8192^3, best of 10",
                      "tensor_frac": (mano_hps * L.F_GEMM / (tf32_peak * 1e12)) if tf32_peak else None,
