@@ -254,8 +254,8 @@ def run_ours(args, rank, world, local_rank):
     bytes_per_sample = step.bytes_per_sample()
 
     # ---- per-family and per-kernel timing (each alone on the current stream, CUDA events) for the roofline ------------
-    # One-chunk batch for the kernels (1024 images = 2048 crops = the launch shape of the backward chunks in the timed
-    # step), so one call == one launch of the kernel in question.  Every leg re-reads inputs far larger than L2.
+    # A 1024-image batch (2048 crops) for the kernels, so one call == one launch of the kernel in question (the timed step
+    # runs the same kernels over 4096-image chunks).  Every leg re-reads inputs far larger than L2.
     from scripts import bench_legs as L
 
     peak, peak_src = peaks()
@@ -337,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    # share of the step: forward launches once per step, the two backward kernels once per 1024-image chunk
+    # share of the step: the per-1024-image launch times scaled to the step's images
     chunks = max(1, (S + 1023) // 1024)
     share = {"pcl_fwd_kernel": fam["pcl_fwd"]["ms"], "pcl_bwd_mid_kernel": kern["pcl_bwd_mid_kernel"]["us_per_launch"] * 1e-3 * chunks,
              "pcl_bwd_img_kernel": kern["pcl_bwd_img_kernel"]["us_per_launch"] * 1e-3 * chunks}

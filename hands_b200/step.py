@@ -55,9 +55,6 @@ class GeometryStep:
             self.params = torch.empty(n, _lib.PCL_PARAM_FLOATS, **f32)
             self.rot = torch.empty(n, 3, 3, **f32)
             self.pcl_ws_bytes = self.lib.hb_pcl_bwd_workspace_bytes(n, hands_per_sample, 3, R)
-            chunk = int(os.environ.get("HB_PCL_CHUNK_IMGS", "0"))
-            if chunk > 0:   # experiment knob: images per backward chunk
-                self.pcl_ws_bytes = self.lib.hb_pcl_bwd_workspace_bytes(min(S, chunk) * hands_per_sample, hands_per_sample, 3, R)
             self.pcl_ws = torch.empty((self.pcl_ws_bytes + 3) // 4, **f32)
             self.mean_s2 = float(((self.bbox[:, 2:] - self.bbox[:, :2]).max(dim=1).values.float() ** 2).mean())
         if with_mano:
