@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libhands_b200.so")
-SOURCES = ["hb_api.cu", "mano_kernels.cu", "mano_tc.cu", "pcl_kernels.cu", "pcl_setup.cu", "loss_kernels.cu"]
+SOURCES = ["hb_api.cu", "mano_kernels.cu", "mano_tc.cu", "pcl_kernels.cu", "pcl_setup.cu", "loss_kernels.cu", "silhouette.cu"]
 PER_FILE_FLAGS = {"pcl_setup.cu": ["-fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

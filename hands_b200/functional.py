@@ -362,3 +362,71 @@ class PerspectiveCropFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.hb_pcl_bwd(_ptr(g_out), _ptr(params), n, cpi, C, R, _ptr(g_img), _ptr(ws), nbytes, _stream()), "hb_pcl_bwd")
         return g_img, None, None, None, None, None
+
+
+class SilhouetteHandle:
+    """Owns one hb_sil* (face table + vertex->corner adjacency of one mesh topology on one CUDA device)."""
+
+    def __init__(self, faces, n_verts, device):
+        lib = _lib.load()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("SilhouetteHandle needs a CUDA device")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        f = torch.as_tensor(faces).detach().to("cpu", torch.int32).contiguous()
+        if f.dim() != 2 or f.shape[1] != 3:
+            raise ValueError(f"faces: expected (F,3), got {tuple(f.shape)}")
+        out = ctypes.c_void_p()
+        _lib.check(lib.hb_sil_create(ctypes.c_void_p(f.data_ptr()), f.shape[0], int(n_verts), idx, ctypes.byref(out)), "hb_sil_create")
+        self.handle = out
+        self.n_faces, self.n_verts = f.shape[0], int(n_verts)
+        self.device = torch.device("cuda", idx)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _lib.load().hb_sil_destroy(h)
+            except Exception:
+                pass
+
+
+class SoftSilhouetteFunction(torch.autograd.Function):
+    """pytorch3d MeshRasterizer + SoftSilhouetteShader as the reference configures them
+    (src/models/hands_light/renderer.py:124-199).  verts_cam (B,V,3), K (B,3,3) -> mask (B,1,S,S).
+    Gradient w.r.t. verts_cam only (intrinsics are data); the backward reads the forward's scratch
+    (face records, per-pixel alpha and depth threshold), so a forward that needs a gradient keeps it."""
+
+    @staticmethod
+    def forward(ctx, handle, verts_cam, K, img_res, sigma, blur_radius):
+        lib = _lib.load()
+        needs_grad = bool(verts_cam.requires_grad)
+        verts_cam = _f32c(verts_cam, "verts_cam", (None, handle.n_verts, 3))
+        B = verts_cam.shape[0]
+        K = _f32c(K, "K", (B, 3, 3))
+        dev = verts_cam.device
+        if dev != handle.device:
+            raise RuntimeError(f"verts_cam is on {dev}, the silhouette handle on {handle.device}")
+        S = int(img_res)
+        mask = torch.empty(B, 1, S, S, dtype=torch.float32, device=dev)
+        nbytes = lib.hb_sil_workspace_bytes(handle.handle, B, S)
+        ws = _workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hb_sil_fwd(handle.handle, _ptr(verts_cam), _ptr(K), B, S, float(sigma), float(blur_radius), _ptr(mask),
+                                      _ptr(ws), nbytes, _stream()), "hb_sil_fwd")
+        if needs_grad:
+            ctx.save_for_backward(verts_cam, K)
+            ctx.ws, ctx.nbytes, ctx.handle, ctx.cfg = ws, nbytes, handle, (B, S, float(sigma), float(blur_radius))
+        return mask
+
+    @staticmethod
+    def backward(ctx, g_mask):
+        lib = _lib.load()
+        verts_cam, K = ctx.saved_tensors
+        B, S, sigma, blur = ctx.cfg
+        g_mask = g_mask.contiguous().float()
+        g_verts = torch.empty_like(verts_cam)
+        with torch.cuda.device(verts_cam.device):
+            _lib.check(lib.hb_sil_bwd(ctx.handle.handle, _ptr(verts_cam), _ptr(K), _ptr(g_mask), B, S, sigma, blur, _ptr(ctx.ws), ctx.nbytes,
+                                      _ptr(g_verts), _stream()), "hb_sil_bwd")
+        return None, g_verts, None, None, None, None

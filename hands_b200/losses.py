@@ -137,6 +137,44 @@ def axis_angle_to_matrix(aa):
     return R.reshape(lead + (3, 3))
 
 
+class MaskL1LossFunction(torch.autograd.Function):
+    """mean over (B, n) of |pred - gt| * valid[b] * gate[b]; gradient w.r.t. pred only."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, valid, gate):
+        B = pred.shape[0]          # (B, n) views: the caller flattens (autograd must see the same shape come back)
+        pred = _f32c(pred, "pred_mask", (None, None))
+        n = pred.shape[1]
+        gt = _f32c(gt.detach().reshape(B, -1).float(), "gt_mask", (B, n))
+        valid = None if valid is None else _f32c(valid.detach().float().reshape(-1), "valid", (B,))
+        gate = None if gate is None else _f32c(gate.detach().float().reshape(-1), "gate", (B,))
+        partial = torch.empty(max(B, 1), dtype=torch.float32, device=pred.device)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            _lib.check(_lib.load().hb_mask_l1_loss_fwd(_ptr(pred), _ptr(gt), _ptr(valid), _ptr(gate), B, n, _ptr(partial), _ptr(loss), _stream()),
+                       "hb_mask_l1_loss_fwd")
+        ctx.save_for_backward(pred, gt, valid, gate)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, gt, valid, gate = ctx.saved_tensors
+        B, n = pred.shape
+        g = g.reshape(1).contiguous().float()
+        g_pred = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            _lib.check(_lib.load().hb_mask_l1_loss_bwd(_ptr(pred), _ptr(gt), _ptr(valid), _ptr(gate), _ptr(g), B, n, _ptr(g_pred), _stream()),
+                       "hb_mask_l1_loss_bwd")
+        return g_pred, None, None, None
+
+
+def render_loss(pred_mask, gt_mask, is_valid, gate=None):
+    """`render_loss(...).mean()` of the reference (src/utils/loss_modules.py:146-152 as used at
+    src/callbacks/loss/loss_arctic_sf.py:177-183, `gate` = meta_info['is_mask_loss']): one fused L1 + reduction."""
+    B = pred_mask.shape[0]
+    return MaskL1LossFunction.apply(pred_mask.reshape(B, -1), gt_mask, is_valid, gate)
+
+
 def compute_loss_light(pred, gt, meta_info, img_res=224):
     """Drop-in for the MANO terms of the reference's `compute_loss_light` (src/callbacks/loss/loss_arctic_sf.py:20-158): same
     dictionary of (loss, weight) pairs under the same keys, every term one fused launch (+ one fixed-order reduction) on the
@@ -157,4 +195,8 @@ def compute_loss_light(pred, gt, meta_info, img_res=224):
         out[f"loss/mano/beta/{side}"] = (vector_loss(pred[f"mano.beta.{side}"], gt[f"mano.beta.{side}"], valid, gates["is_beta_loss"]).view(-1), 0.001)
     out["loss/mano/transl/l"] = (vector_loss(pred["mano.cam_t.wp.l"], gt["mano.cam_t.wp.l"], rv, gates["is_cam_loss"], pred_minus=pred["mano.cam_t.wp.r"],
                                              gt_minus=gt["mano.cam_t.wp.r"], valid2=lv).view(-1), 1.0)
+    if "render.r" in pred and "render.r" in gt:   # args.use_render_seg_loss (loss_arctic_sf.py:172-183)
+        gate = meta_info["is_mask_loss"].float() if "is_mask_loss" in meta_info else None
+        for side in ("r", "l"):
+            out[f"loss/mask/{side}"] = (render_loss(pred[f"render.{side}"], gt[f"render.{side}"], gt[f"render_valid_{side}"], gate).view(-1), 10.0)
     return out

@@ -131,3 +131,62 @@ def synthetic_pcl_inputs(B, seed=0, img_res=224, smin=56, smax=168, smooth=False
     K[:, 1, 2] = img_res / 2
     K[:, 2, 2] = 1.0
     return img.contiguous(), bbox.contiguous(), K.contiguous()
+
+
+def synthetic_tube_mesh(seed=0):
+    """A hand-sized closed-ended tube with MANO's own counts and topology class -- 778 vertices, 1538 faces, one open
+    boundary ring of 16 vertices (the wrist; MANO: common/body_models.py:35-63) -- for the silhouette renderer, whose
+    cost and coverage depend on the triangles being local (the random `faces` of `synthetic_mano_buffers` are not).
+    48 rings of 16 vertices + a cap of 8 + 2 vertices.  Returns verts (778,3) fp32 in metres, centred, long axis = y,
+    and faces (1538,3) int64."""
+    g = torch.Generator().manual_seed(3000 + seed)
+    rings, seg = 48, 16
+    k = torch.arange(rings, dtype=torch.float64)
+    u = k / (rings - 1)
+    y = -0.085 + 0.15 * u
+    rad = 0.036 * (1.0 - 0.45 * u) * (1.0 + 0.12 * torch.sin(3.0 * math.pi * u))
+    th = torch.arange(seg, dtype=torch.float64) * (2.0 * math.pi / seg)
+    bend = 0.02 * u * u
+    ring = torch.stack([rad[:, None] * torch.cos(th)[None], y[:, None].expand(rings, seg), 0.45 * rad[:, None] * torch.sin(th)[None] + bend[:, None]], -1)
+    th8 = th[0::2] + math.pi / seg
+    mid = torch.stack([0.55 * rad[-1] * torch.cos(th8), torch.full((8,), float(y[-1]) + 0.006, dtype=torch.float64), 0.45 * 0.55 * rad[-1] * torch.sin(th8) + bend[-1]], -1)
+    ctr = torch.tensor([[0.004, float(y[-1]) + 0.009, float(bend[-1])], [-0.004, float(y[-1]) + 0.009, float(bend[-1])]], dtype=torch.float64)
+    verts = torch.cat([ring.reshape(-1, 3), mid, ctr], 0)
+    verts = verts + 2e-4 * torch.randn(verts.shape, generator=g, dtype=torch.float64)
+    faces = []
+    for r in range(rings - 1):
+        for s in range(seg):
+            a, b = r * seg + s, r * seg + (s + 1) % seg
+            faces += [[a, b, a + seg], [b, b + seg, a + seg]]
+    o = lambda i: (rings - 1) * seg + i % seg   # noqa: E731  last ring
+    m = lambda i: rings * seg + i % 8           # noqa: E731
+    c0, c1 = rings * seg + 8, rings * seg + 9
+    for i in range(8):
+        faces += [[o(2 * i), o(2 * i + 1), m(i)], [o(2 * i + 1), o(2 * i + 2), m(i)], [o(2 * i + 2), m(i + 1), m(i)]]
+    # th8[0..1] and th8[6..7] face +x (c0), th8[2..5] face -x (c1)
+    faces += [[m(i), m(i + 1), c0] for i in (6, 7, 0)] + [[m(i), m(i + 1), c1] for i in (2, 3, 4)]
+    faces += [[m(1), m(2), c1], [m(1), c1, c0], [m(5), m(6), c0], [m(5), c0, c1]]
+    verts = verts - verts.mean(0, keepdim=True)
+    faces = torch.tensor(faces, dtype=torch.int64)
+    assert verts.shape == (NUM_VERTS, 3) and faces.shape == (NUM_FACES, 3)
+    return verts.float().contiguous(), faces.contiguous()
+
+
+def synthetic_silhouette_inputs(B, seed=0, img_res=224):
+    """verts_cam (B,778,3): the tube mesh under a random rotation, 0.45-0.9 m in front of the camera, projected centre
+    within the middle of the image; faces (1538,3); K (B,3,3) with f ~ U(500, 900)."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    verts, faces = synthetic_tube_mesh(0)
+    R = random_rotmats(B, g).reshape(B, 3, 3)
+    f = torch.rand(B, generator=g) * 400.0 + 500.0
+    z = torch.rand(B, generator=g) * 0.45 + 0.45
+    cxy = (torch.rand(B, 2, generator=g) - 0.5) * 0.3 * img_res   # pixel offset of the hand centre
+    t = torch.stack([cxy[:, 0] * z / f, cxy[:, 1] * z / f, z], -1)
+    vc = torch.einsum("bij,vj->bvi", R, verts) + t[:, None]
+    K = torch.zeros(B, 3, 3)
+    K[:, 0, 0] = f
+    K[:, 1, 1] = f
+    K[:, 0, 2] = img_res / 2
+    K[:, 1, 2] = img_res / 2
+    K[:, 2, 2] = 1.0
+    return vc.float().contiguous(), faces, K.contiguous()

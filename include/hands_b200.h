@@ -53,7 +53,7 @@ typedef struct hb_mano hb_mano; /* opaque: MANO constants of one hand side on on
 #define HB_ROT6D_COLS 1        /* src/models/hamer_light/geometry.py:47-62, src/models/handoccnet_light/mano_head.py:132-141: a1=x[0:3], a2=x[3:6], COLUMNS */
 #define HB_ROT6D_COLS_PAIRED 2 /* common/rot.py:367-381: a1=x[0,2,4], a2=x[1,3,5], COLUMNS */
 
-#define HB_VERSION 200 /* hb_version() of a matching binary */
+#define HB_VERSION 201 /* hb_version() of a matching binary */
 const char* hb_last_error_string(void);
 int hb_version(void);
 
@@ -244,6 +244,35 @@ int hb_pcl_bwd(const float* g_out, const float* params, int n_crops, int crops_p
  * meaningful stage by stage when the whole batch fits one chunk of the workspace. */
 int hb_pcl_bwd_stages(const float* g_out, const float* params, int n_crops, int crops_per_img, int C, int img_res,
                       float* g_img, void* workspace, size_t workspace_bytes, int stages, void* stream);
+
+/* ---- soft silhouette of the hand mesh -----------------------------------------------------------
+ * Replaces: src/models/hands_light/renderer.py:124-199 (pytorch3d MeshRasterizer + SoftSilhouetteShader as configured at
+ *   :128-139, cameras built at :187-191, flip_transpose_canvas :201-209) — the consumer of mano.v3d.cam.{r,l} behind
+ *   `use_render_seg_loss` (src/models/hands_light/model.py:413-420, src/callbacks/loss/loss_arctic_sf.py:172-183).
+ * mask[b,0,r,c] = 1 - prod_k (1 - sigmoid(-d_k / sigma)) over the HB_SIL_FACES_PER_PIXEL candidate faces of smallest
+ *   (clipped-barycentric) depth at the pixel centre (c+0.5, r+0.5) of the K-projected image; d_k = squared NDC distance to
+ *   the face's nearest edge, negative inside; candidates = inside, or closer than blur_radius.
+ * The handle owns the face table (host int32 (n_faces,3) at creation) and a vertex->corner adjacency for the backward. */
+typedef struct hb_sil hb_sil;
+#define HB_SIL_FACES_PER_PIXEL 10
+#define HB_SIL_MAX_FACES 12000
+int hb_sil_create(const int32_t* faces_host, int n_faces, int n_verts, int device, hb_sil** out);
+int hb_sil_destroy(hb_sil* h);
+/* Caller-owned scratch shared by forward and backward: face records (80 B/face), (alpha, depth threshold) per pixel,
+ *   per-face corner gradients.  hb_sil_bwd must see the workspace exactly as hb_sil_fwd of the same inputs left it. */
+size_t hb_sil_workspace_bytes(const hb_sil* h, int n_meshes, int img_res);
+/* verts_cam (n_meshes, n_verts, 3) camera space; K (n_meshes,3,3) pixel intrinsics; mask (n_meshes,1,img_res,img_res). */
+int hb_sil_fwd(const hb_sil* h, const float* verts_cam, const float* K, int n_meshes, int img_res, float sigma,
+               float blur_radius, float* mask, void* workspace, size_t workspace_bytes, void* stream);
+/* g_mask (n_meshes,1,img_res,img_res) -> g_verts (n_meshes,n_verts,3), every element written once (no atomics). */
+int hb_sil_bwd(const hb_sil* h, const float* verts_cam, const float* K, const float* g_mask, int n_meshes, int img_res,
+               float sigma, float blur_radius, void* workspace, size_t workspace_bytes, float* g_verts, void* stream);
+/* render_loss (src/utils/loss_modules.py:146-152) gated as in loss_arctic_sf.py:177-183: loss = mean over (B, n) of
+ *   |pred - gt| * valid[b] * gate[b] (valid / gate may be NULL = 1).  partial (B) scratch; fixed-order reductions. */
+int hb_mask_l1_loss_fwd(const float* pred, const float* gt, const float* valid, const float* gate, int B, int n,
+                        float* partial, float* loss, void* stream);
+int hb_mask_l1_loss_bwd(const float* pred, const float* gt, const float* valid, const float* gate, const float* g_loss,
+                        int B, int n, float* g_pred, void* stream);
 
 /* ---- counters ---------------------------------------------------------------------------------
  * Number of kernels this library has launched since load (all threads). bench.py reports the delta. */

@@ -123,7 +123,7 @@ def test_stale_binary_detection_uses_source_digest(monkeypatch):
     assert _build.needs_build()
     monkeypatch.undo()
     assert not _build.needs_build()
-    assert _lib.load().hb_version() == _build.header_version() == 200
+    assert _lib.load().hb_version() == _build.header_version() >= 201
 
 
 def test_cpu_baseline_legs_run():
