@@ -224,25 +224,35 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
     float qz[SIL_K], qd[SIL_K];
 #pragma unroll
     for (int k = 0; k < SIL_K; ++k) { qz[k] = INFINITY; qd[k] = 0.0f; }
-    for (int j = 0; j < nt; ++j) {
-      const float4* Rf = R + (int)tlist[j] * SIL_REC;
-      const float4 d = __ldg(Rf + 3);
-      const float yhi = __ldg(Rf + 4).x;
-      if (d.y > fx1 || d.z < fx0 || d.w > fy1 || yhi < fy0) continue;   // warp-uniform: the face misses the footprint
-      if (px > d.z || px < d.y || py > yhi || py < d.w) continue;
-      const SilFace f = load_face(Rf);
-      SilHit h;
-      if (!sil_eval(f, px, py, blur, h)) continue;
-      float z = h.pz, sd = h.inside ? -h.dist : h.dist;
-      if (z < qz[SIL_K - 1]) {   // sorted insertion; a tie stays behind the earlier face
+    for (int base = 0; base < nt; base += 32) {
+      // 32 faces of the tile list against the warp's footprint at once; the survivors are visited in list order
+      const int j = base + lane;
+      int fidx = 0;
+      bool hit = false;
+      if (j < nt) {
+        fidx = tlist[j];
+        const float4 d = __ldg(R + fidx * SIL_REC + 3);
+        const float yhi = __ldg(R + fidx * SIL_REC + 4).x;
+        hit = !(d.y > fx1 || d.z < fx0 || d.w > fy1 || yhi < fy0);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const SilFace f = load_face(R + __shfl_sync(0xffffffffu, fidx, src) * SIL_REC);
+        SilHit h;
+        if (!sil_eval(f, px, py, blur, h)) continue;
+        float z = h.pz, sd = h.inside ? -h.dist : h.dist;
+        if (z < qz[SIL_K - 1]) {   // sorted insertion; a tie stays behind the earlier face
 #pragma unroll
-        for (int k = 0; k < SIL_K; ++k) {
-          const bool sw = z < qz[k];
-          const float tz = qz[k], td = qd[k];
-          qz[k] = sw ? z : tz;
-          qd[k] = sw ? sd : td;
-          z = sw ? tz : z;
-          sd = sw ? td : sd;
+          for (int k = 0; k < SIL_K; ++k) {
+            const bool sw = z < qz[k];
+            const float tz = qz[k], td = qd[k];
+            qz[k] = sw ? z : tz;
+            qd[k] = sw ? sd : td;
+            z = sw ? tz : z;
+            sd = sw ? td : sd;
+          }
         }
       }
     }

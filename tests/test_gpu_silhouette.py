@@ -6,8 +6,9 @@ The oracle restates pytorch3d's published algorithm; pytorch3d is absent: PARITY
 Tolerances.  The blend evaluates sigmoid(d^2 / 1e-5) of a squared NDC distance: one fp32 ulp of a vertex or pixel
 coordinate (6e-8 at |x| ~ 1) moves d^2 by up to 2 * 0.0117 * 6e-8 = 1.4e-9, i.e. the sigmoid's argument by 1.4e-4 and
 the mask by <= 3.5e-5 per fragment -- so fp32 implementations that order their operations differently (torch's bmm,
-pytorch3d's kernel, this one) agree to ~1e-4 absolute on the mask, not better, and the same factor relative on the
-gradients.  Stated: mask 2e-4 absolute vs the fp32 oracle; gradients 2e-3 of the largest component vs the fp64 oracle
+pytorch3d's kernel, this one) can differ by up to ~1e-4 absolute on the mask and the same factor relative on the gradients
+in the worst case.  Stated: mask 5e-5 absolute vs the fp32 oracle (measured 7e-6); gradients 5e-4 of the largest component
+vs the fp64 oracle (measured 2e-5 .. 7e-5)
 (the analytic backward of the fp64 forward, itself checked against central differences on CPU).
 
 Depth selection.  With more than faces_per_pixel = 10 candidates at a pixel (19 % of the covered pixels of the test meshes)
@@ -68,8 +69,8 @@ def test_forward_matches_oracle_on_the_hand_sized_mesh(dev):
     assert selecting.sum() > 0.05 * (cnt > 0).sum()           # the depth selection is exercised, not a corner case
     tied = selecting & (gap <= 1e-6)
     err = np.abs(got - ref32)
-    tol_check("silhouette mask vs fp32 oracle, <= 10 candidates (abs)", err[~selecting].max(), 2e-4)
-    tol_check("silhouette mask vs fp32 oracle, depth selection active (abs)", err[selecting & ~tied].max(), 2e-4)
+    tol_check("silhouette mask vs fp32 oracle, <= 10 candidates (abs)", err[~selecting].max(), 5e-5)
+    tol_check("silhouette mask vs fp32 oracle, depth selection active (abs)", err[selecting & ~tied].max(), 5e-5)
     assert tied.sum() < 0.01 * (cnt > 0).sum() and err[tied].max() < 0.1 and err[tied].mean() < 2e-3
     assert np.abs(got - ref64).mean() < 2e-6
 
@@ -86,14 +87,14 @@ def test_backward_matches_fp64_oracle(dev):
     gv = gv.cpu().numpy().astype(np.float64)
     assert np.abs(ref).max() > 100.0
     for b in range(2):
-        tol_check(f"silhouette g_verts[{b}] vs fp64 oracle (rel to max)", np.abs(gv[b] - ref[b]).max() / np.abs(ref[b]).max(), 2e-3)
+        tol_check(f"silhouette g_verts[{b}] vs fp64 oracle (rel to max)", np.abs(gv[b] - ref[b]).max() / np.abs(ref[b]).max(), 5e-4)
     # the L1 mask loss's own upstream gradient (sign pattern) as well
     gt = (rng.random((2, 1, 224, 224)) > 0.5).astype(np.float32)
     m = so.soft_silhouette(vc.numpy(), faces.numpy(), K.numpy(), 224, dtype=np.float64)
     gl = np.sign(m - gt) * well / m.size
     _, gv2 = render(vc, faces, K, 224, dev, gl.astype(np.float32))
     ref2 = so.soft_silhouette_backward(vc.numpy().astype(np.float64), faces.numpy(), K.numpy().astype(np.float64), gl, 224)
-    tol_check("silhouette g_verts under the L1 mask loss (rel to max)", np.abs(gv2.cpu().numpy() - ref2).max() / np.abs(ref2).max(), 2e-3)
+    tol_check("silhouette g_verts under the L1 mask loss (rel to max)", np.abs(gv2.cpu().numpy() - ref2).max() / np.abs(ref2).max(), 5e-4)
 
 
 def _tri(px, S=32, f=40.0):
@@ -191,7 +192,7 @@ def test_mano_renderer_dropin_and_mask_loss(dev):
     m = out["mask"].detach().cpu().numpy()
     gl = (np.sign(m - gt.cpu().numpy()) * (valid * gate).cpu().numpy()[:, None, None, None]) / m.size
     ref_g = so.soft_silhouette_backward(vc.numpy().astype(np.float64), faces.numpy(), K.numpy().astype(np.float64), gl.astype(np.float64), 224)
-    tol_check("MANORenderer + render_loss g_verts (rel to max)", np.abs(v.grad.cpu().numpy() - ref_g).max() / np.abs(ref_g).max(), 2e-3)
+    tol_check("MANORenderer + render_loss g_verts (rel to max)", np.abs(v.grad.cpu().numpy() - ref_g).max() / np.abs(ref_g).max(), 5e-4)
 
 
 def test_abi_errors(dev):
