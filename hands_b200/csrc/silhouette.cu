@@ -5,8 +5,9 @@
 // oracle/silhouette_oracle.py ("parity unpinned").
 //
 // Forward:  sil_setup_kernel   thread = (hand, face): project the three corners, build an 80-byte face record
-//           sil_raster_kernel  CTA = (hand, band of 16 rows): faces culled to the band, then to each 16x16 tile, by
-//                              ordered compaction (face order is the tie-break of the depth selection); thread = pixel
+//           sil_raster_kernel  CTA = (hand, band of 16 rows): faces culled to the band by ordered compaction (face order
+//                              is the tie-break of the depth selection), then per warp footprint (8x4 pixels, handed
+//                              out dynamically) 32 faces per ballot; thread = pixel
 //                              keeps the K nearest candidates sorted in registers; writes the mask and, for the
 //                              backward, (alpha, depth of the K-th fragment) per pixel.
 // Backward: sil_face_bwd_kernel   warp = (hand, face): walks the face's pixel box, re-evaluates the SAME device function
@@ -41,20 +42,18 @@ __device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay,
   return __fsub_rn(__fmul_rn(__fsub_rn(px, ax), __fsub_rn(by, ay)), __fmul_rn(__fsub_rn(py, ay), __fsub_rn(bx, ax)));
 }
 
-// squared distance from p to the segment ab; tt = clamped parameter (PointLineDistanceForward)
-__device__ __forceinline__ float seg_dist(float px, float py, float ax, float ay, float bx, float by, float il, float& tt, float& dx, float& dy) {
+// squared distance from p to the segment a + t e, t in [0,1]; (dx,dy) = p - a in, p - p_proj out; tt = clamped parameter
+// (PointLineDistanceForward).  il = 1/|e|^2, or -1 for a degenerate edge (distance to its end point b = a + e).
+__device__ __forceinline__ float seg_dist(float ex, float ey, float il, float& dx, float& dy, float& tt) {
   if (il < 0.0f) {
     tt = 1.0f;
-    dx = __fsub_rn(px, bx);
-    dy = __fsub_rn(py, by);
   } else {
-    const float bax = __fsub_rn(bx, ax), bay = __fsub_rn(by, ay);
-    const float t = __fmul_rn(__fadd_rn(__fmul_rn(bax, __fsub_rn(px, ax)), __fmul_rn(bay, __fsub_rn(py, ay))), il);
+    const float t = __fmul_rn(__fmaf_rn(ex, dx, __fmul_rn(ey, dy)), il);
     tt = fminf(fmaxf(t, 0.0f), 1.0f);
-    dx = __fsub_rn(px, __fmaf_rn(tt, bax, ax));
-    dy = __fsub_rn(py, __fmaf_rn(tt, bay, ay));
   }
-  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  dx = __fmaf_rn(-tt, ex, dx);
+  dy = __fmaf_rn(-tt, ey, dy);
+  return __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
 }
 
 struct SilHit {
@@ -63,28 +62,39 @@ struct SilHit {
 };
 
 // CheckPixelInsideFace without the selection bookkeeping.  false = the face is no candidate at this pixel.
+// Every operation is an explicit round-to-nearest intrinsic: forward and backward kernels inline this function separately
+// and must agree to the bit on pz (the selection test) and on the distances.
 __device__ __forceinline__ bool sil_eval(const SilFace& f, float px, float py, float blur, SilHit& h) {
   if (px > f.xhi || px < f.xlo || py > f.yhi || py < f.ylo) return false;
-  const float w0 = __fmul_rn(edge_fn(px, py, f.v1x, f.v1y, f.v2x, f.v2y), f.inv_area);
-  const float w1 = __fmul_rn(edge_fn(px, py, f.v2x, f.v2y, f.v0x, f.v0y), f.inv_area);
-  const float w2 = __fmul_rn(edge_fn(px, py, f.v0x, f.v0y, f.v1x, f.v1y), f.inv_area);
+  const float e01x = __fsub_rn(f.v1x, f.v0x), e01y = __fsub_rn(f.v1y, f.v0y);
+  const float e02x = __fsub_rn(f.v2x, f.v0x), e02y = __fsub_rn(f.v2y, f.v0y);
+  const float e12x = __fsub_rn(f.v2x, f.v1x), e12y = __fsub_rn(f.v2y, f.v1y);
+  const float p0x = __fsub_rn(px, f.v0x), p0y = __fsub_rn(py, f.v0y);
+  const float p1x = __fsub_rn(px, f.v1x), p1y = __fsub_rn(py, f.v1y);
+  const float p2x = __fsub_rn(px, f.v2x), p2y = __fsub_rn(py, f.v2y);
+  // barycentric coordinates: edge(p; v1,v2), edge(p; v2,v0), edge(p; v0,v1) over the face's edge(v2; v0,v1) + eps
+  const float w0 = __fmul_rn(__fmaf_rn(p1x, e12y, -__fmul_rn(p1y, e12x)), f.inv_area);
+  const float w1 = __fmul_rn(__fmaf_rn(p2y, e02x, -__fmul_rn(p2x, e02y)), f.inv_area);
+  const float w2 = __fmul_rn(__fmaf_rn(p0x, e01y, -__fmul_rn(p0y, e01x)), f.inv_area);
+  h.inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
+  float dx, dy, tt;
+  dx = p0x; dy = p0y;
+  h.d01 = seg_dist(e01x, e01y, f.il01, dx, dy, tt);
+  dx = p0x; dy = p0y;
+  h.d02 = seg_dist(e02x, e02y, f.il02, dx, dy, tt);
+  dx = p1x; dy = p1y;
+  h.d12 = seg_dist(e12x, e12y, f.il12, dx, dy, tt);
+  h.dist = fminf(fminf(h.d01, h.d02), h.d12);
+  if (!(h.inside || h.dist < blur)) return false;
   const float c0 = fminf(fmaxf(w0, 0.0f), 1.0f), c1 = fminf(fmaxf(w1, 0.0f), 1.0f), c2 = fminf(fmaxf(w2, 0.0f), 1.0f);
   const float inv = __frcp_rn(fmaxf(__fadd_rn(__fadd_rn(c0, c1), c2), 1e-5f));
-  h.pz = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(c0, inv), f.z0), __fmul_rn(__fmul_rn(c1, inv), f.z1)), __fmul_rn(__fmul_rn(c2, inv), f.z2));
-  if (!(h.pz >= 0.0f)) return false;
-  float tt, dx, dy;
-  h.d01 = seg_dist(px, py, f.v0x, f.v0y, f.v1x, f.v1y, f.il01, tt, dx, dy);
-  h.d02 = seg_dist(px, py, f.v0x, f.v0y, f.v2x, f.v2y, f.il02, tt, dx, dy);
-  h.d12 = seg_dist(px, py, f.v1x, f.v1y, f.v2x, f.v2y, f.il12, tt, dx, dy);
-  h.dist = fminf(fminf(h.d01, h.d02), h.d12);
-  h.inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
-  return h.inside || h.dist < blur;
+  h.pz = __fmul_rn(__fmaf_rn(c2, f.z2, __fmaf_rn(c1, f.z1, __fmul_rn(c0, f.z0))), inv);
+  return h.pz >= 0.0f;
 }
 
 // sigmoid(-sd / sigma) as torch evaluates it in fp32
-__device__ __forceinline__ float sil_prob(float sd, float sigma) {
-  const float x = __fdiv_rn(-sd, sigma);
-  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+__device__ __forceinline__ float sil_prob(float sd, float inv_sigma) {
+  return __frcp_rn(__fadd_rn(1.0f, expf(__fmul_rn(sd, inv_sigma))));
 }
 
 __device__ __forceinline__ SilFace load_face(const float4* __restrict__ R) {
@@ -188,14 +198,15 @@ __device__ __forceinline__ int compact_ordered(int n, Keep keep, unsigned short*
 
 __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restrict__ rec, int F, int S, float sigma, float blur,
                                                          float* __restrict__ mask, float2* __restrict__ frag) {
-  extern __shared__ unsigned short s_list[];   // band list [F], tile list [F]
+  extern __shared__ float s_dyn[];              // pixel-centre table [S + 16], then the band list [F] (unsigned short)
   __shared__ int s_wc[8];
-  unsigned short* blist = s_list;
-  unsigned short* tlist = s_list + F;
+  float* pn = s_dyn;
+  unsigned short* blist = reinterpret_cast<unsigned short*>(s_dyn + S + 16);
   const int b = blockIdx.y, r0 = blockIdx.x * SIL_TILE;
   const float4* R = rec + (size_t)b * F * SIL_REC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float Sf = (float)S;
+  const float Sf = (float)S, inv_sigma = 1.0f / sigma;
+  for (int i = tid; i < S + 16; i += 256) pn[i] = pix_to_ndc(i, Sf);   // one IEEE division per entry instead of per pixel
 
   const int nb = compact_ordered(F, [&](int i, int& val) {
     const int rows = __float_as_int(__ldg(&R[i * SIL_REC + 4]).z);
@@ -203,34 +214,31 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
     return (rows & 0xffff) < r0 + SIL_TILE && (rows >> 16) > r0;
   }, blist, s_wc);
 
-  // warp footprint inside a tile: 8 columns x 4 rows
-  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
-  const int row = r0 + wy + (lane >> 3);
-  const float py = pix_to_ndc(row, Sf);
-  const float fy0 = pix_to_ndc(r0 + wy, Sf), fy1 = pix_to_ndc(r0 + wy + 3, Sf);
-
-  for (int c0 = 0; c0 < S; c0 += SIL_TILE) {
-    int nt = 0;
-    if (nb > 0) {
-      nt = compact_ordered(nb, [&](int i, int& val) {
-        val = blist[i];
-        const int cols = __float_as_int(__ldg(&R[val * SIL_REC + 4]).y);
-        return (cols & 0xffff) < c0 + SIL_TILE && (cols >> 16) > c0;
-      }, tlist, s_wc);
-    }
-    const int col = c0 + wx + (lane & 7);
-    const float px = pix_to_ndc(col, Sf);
-    const float fx0 = pix_to_ndc(c0 + wx, Sf), fx1 = pix_to_ndc(c0 + wx + 7, Sf);
+  // Footprints of 8 columns x 4 rows (one warp each), handed out dynamically: the band's warps never wait for each other
+  // (which warp renders a footprint does not change its pixels).
+  __shared__ int s_next;
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  const int fcols = (S + 7) / 8, nfp = fcols * (SIL_TILE / 4);
+  for (;;) {
+    int fp = 0;
+    if (lane == 0) fp = atomicAdd(&s_next, 1);
+    fp = __shfl_sync(0xffffffffu, fp, 0);
+    if (fp >= nfp) break;
+    const int fr = r0 + (fp / fcols) * 4, fc = (fp % fcols) * 8;
+    const int row = fr + (lane >> 3), col = fc + (lane & 7);
+    const float px = pn[col], py = pn[row];
+    const float fx0 = pn[fc], fx1 = pn[fc + 7], fy0 = pn[fr], fy1 = pn[fr + 3];
     float qz[SIL_K], qd[SIL_K];
 #pragma unroll
     for (int k = 0; k < SIL_K; ++k) { qz[k] = INFINITY; qd[k] = 0.0f; }
-    for (int base = 0; base < nt; base += 32) {
-      // 32 faces of the tile list against the warp's footprint at once; the survivors are visited in list order
+    for (int base = 0; base < nb; base += 32) {
+      // 32 faces of the band list against the footprint at once; the survivors are visited in list (= face) order
       const int j = base + lane;
       int fidx = 0;
       bool hit = false;
-      if (j < nt) {
-        fidx = tlist[j];
+      if (j < nb) {
+        fidx = blist[j];
         const float4 d = __ldg(R + fidx * SIL_REC + 3);
         const float yhi = __ldg(R + fidx * SIL_REC + 4).x;
         hit = !(d.y > fx1 || d.z < fx0 || d.w > fy1 || yhi < fy0);
@@ -259,18 +267,20 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
     float alpha = 1.0f;
 #pragma unroll
     for (int k = 0; k < SIL_K; ++k)
-      if (qz[k] < INFINITY) alpha = __fmul_rn(alpha, __fsub_rn(1.0f, sil_prob(qd[k], sigma)));
+      if (qz[k] < INFINITY) alpha = __fmul_rn(alpha, __fsub_rn(1.0f, sil_prob(qd[k], inv_sigma)));
     if (row < S && col < S) {
       const size_t o = ((size_t)b * S + row) * S + col;
       mask[o] = __fsub_rn(1.0f, alpha);
       frag[o] = make_float2(alpha, qz[SIL_K - 1]);
     }
-    __syncthreads();   // tlist is rewritten by the next tile's compaction
   }
 }
 
 __global__ void __launch_bounds__(256) sil_face_bwd_kernel(const float4* __restrict__ rec, const float2* __restrict__ frag, const float* __restrict__ g_mask,
                                                            int F, int S, float sigma, float blur, float* __restrict__ gface) {
+  extern __shared__ float pn[];   // pixel-centre table [S]
+  for (int i = threadIdx.x; i < S; i += 256) pn[i] = pix_to_ndc(i, (float)S);
+  __syncthreads();
   const int lane = threadIdx.x & 31, f = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
   if (f >= F) return;
   const float4* Rf = rec + ((size_t)b * F + f) * SIL_REC;
@@ -279,25 +289,26 @@ __global__ void __launch_bounds__(256) sil_face_bwd_kernel(const float4* __restr
   const int cols = __float_as_int(e.y), rows = __float_as_int(e.z);
   const int clo = cols & 0xffff, w = (cols >> 16) - clo, rlo = rows & 0xffff, hgt = (rows >> 16) - rlo;
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float Sf = (float)S;
-  const float inv_sigma_neg = -1.0f / sigma;
+  const float inv_sigma = 1.0f / sigma;
   if (w > 0 && hgt > 0) {
     const int n = w * hgt;
+    const unsigned magic = w > 1 ? 0xFFFFFFFFu / (unsigned)w + 1u : 0u;   // i / w for i * w < 2^32
     for (int i = lane; i < n; i += 32) {
-      const int r = rlo + i / w, c = clo + i % w;
+      const int q = w > 1 ? (int)__umulhi((unsigned)i, magic) : i;
+      const int r = rlo + q, c = clo + (i - q * w);
       const size_t o = ((size_t)b * S + r) * S + c;
       const float g = __ldg(g_mask + o);
       const float2 fr = __ldg(frag + o);
       const float ga = __fmul_rn(g, fr.x);
       if (ga == 0.0f) continue;
-      const float px = pix_to_ndc(c, Sf), py = pix_to_ndc(r, Sf);
+      const float px = pn[c], py = pn[r];
       SilHit h;
       if (!sil_eval(fc, px, py, blur, h)) continue;
       if (!(h.pz <= fr.y)) continue;                      // the face was not among the pixel's K nearest
       const float sd = h.inside ? -h.dist : h.dist;
-      const float p = sil_prob(sd, sigma);
+      const float p = sil_prob(sd, inv_sigma);
       // d mask / d sd = prod_{m != k}(1 - p_m) * (-p (1 - p) / sigma) = -alpha * p / sigma ; then signed -> absolute distance
-      float gd = ga * p * inv_sigma_neg;
+      float gd = -ga * p * inv_sigma;
       if (h.inside) gd = -gd;
       // PointTriangleDistanceBackward: the nearest edge, ties resolved e01, e02, e12
       int ia, ib;
@@ -305,8 +316,8 @@ __global__ void __launch_bounds__(256) sil_face_bwd_kernel(const float4* __restr
       if (h.d01 <= h.d02 && h.d01 <= h.d12) { ia = 0; ib = 1; ax = fc.v0x; ay = fc.v0y; bx = fc.v1x; by = fc.v1y; il = fc.il01; }
       else if (h.d02 <= h.d01 && h.d02 <= h.d12) { ia = 0; ib = 2; ax = fc.v0x; ay = fc.v0y; bx = fc.v2x; by = fc.v2y; il = fc.il02; }
       else { ia = 1; ib = 2; ax = fc.v1x; ay = fc.v1y; bx = fc.v2x; by = fc.v2y; il = fc.il12; }
-      float tt, dx, dy;
-      seg_dist(px, py, ax, ay, bx, by, il, tt, dx, dy);   // (dx,dy) = p - p_proj
+      float tt, dx = __fsub_rn(px, ax), dy = __fsub_rn(py, ay);
+      seg_dist(__fsub_rn(bx, ax), __fsub_rn(by, ay), il, dx, dy, tt);   // (dx,dy) = p - p_proj
       const float sx = -2.0f * gd * dx, sy = -2.0f * gd * dy;   // gd * 2 * (p_proj - p)
       const float wa = il < 0.0f ? 0.0f : 1.0f - tt, wb = il < 0.0f ? 1.0f : tt;
 #pragma unroll
@@ -489,7 +500,7 @@ extern "C" int hb_sil_fwd(const hb_sil* h, const float* verts_cam, const float* 
   sil_setup_kernel<<<dim3((h->F + 127) / 128, n_meshes), 128, 0, st>>>(verts_cam, K, h->faces, h->F, h->V, img_res, sqrtf(blur_radius), w.rec);
   ++g_launches;
   if (int rc = check_launch("sil_setup_kernel")) return rc;
-  sil_raster_kernel<<<dim3((img_res + SIL_TILE - 1) / SIL_TILE, n_meshes), 256, 2 * sizeof(unsigned short) * h->F, st>>>(w.rec, h->F, img_res, sigma, blur_radius, mask, w.frag);
+  sil_raster_kernel<<<dim3((img_res + SIL_TILE - 1) / SIL_TILE, n_meshes), 256, sizeof(float) * (img_res + 16) + sizeof(unsigned short) * h->F, st>>>(w.rec, h->F, img_res, sigma, blur_radius, mask, w.frag);
   ++g_launches;
   return check_launch("sil_raster_kernel");
 }
@@ -501,7 +512,7 @@ extern "C" int hb_sil_bwd(const hb_sil* h, const float* verts_cam, const float* 
   if (n_meshes == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const SilWs w = sil_ws(h, n_meshes, img_res, workspace);
-  sil_face_bwd_kernel<<<dim3((h->F + 7) / 8, n_meshes), 256, 0, st>>>(w.rec, w.frag, g_mask, h->F, img_res, sigma, blur_radius, w.gface);
+  sil_face_bwd_kernel<<<dim3((h->F + 7) / 8, n_meshes), 256, sizeof(float) * img_res, st>>>(w.rec, w.frag, g_mask, h->F, img_res, sigma, blur_radius, w.gface);
   ++g_launches;
   if (int rc = check_launch("sil_face_bwd_kernel")) return rc;
   sil_vertex_bwd_kernel<<<dim3((h->V + 127) / 128, n_meshes), 128, 0, st>>>(verts_cam, K, w.gface, h->adj_off, h->adj, h->F, h->V, img_res, g_verts);
