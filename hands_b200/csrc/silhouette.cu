@@ -120,12 +120,18 @@ __device__ __forceinline__ SilCam sil_cam(const float* __restrict__ K, float c) 
   return k;
 }
 
-// conservative pixel index range of the NDC interval [lo, hi] (the exact float test is repeated per pixel)
+// exact pixel index range [ilo, ihi] of the centres inside the NDC interval [lo, hi]: an estimate from the inverse map,
+// then stepped against the very pix_to_ndc values the per-pixel test compares with (empty: ilo > ihi)
 __device__ __forceinline__ void pix_range(float lo, float hi, int S, int& ilo, int& ihi) {
-  const float a = floorf((lo + 1.0f) * 0.5f * (float)S - 0.5f) - 1.0f;
-  const float b = ceilf((hi + 1.0f) * 0.5f * (float)S - 0.5f) + 1.0f;
-  ilo = (int)fminf(fmaxf(a, 0.0f), (float)S);        // S = "past the end"
-  ihi = (int)fminf(fmaxf(b, -1.0f), (float)(S - 1));
+  const float Sf = (float)S;
+  int a = (int)fminf(fmaxf(ceilf((lo + 1.0f) * 0.5f * Sf - 0.5f), 0.0f), Sf);
+  int b = (int)fminf(fmaxf(floorf((hi + 1.0f) * 0.5f * Sf - 0.5f), -1.0f), Sf - 1.0f);
+  while (a > 0 && pix_to_ndc(a - 1, Sf) >= lo) --a;
+  while (a < S && pix_to_ndc(a, Sf) < lo) ++a;
+  while (b < S - 1 && pix_to_ndc(b + 1, Sf) <= hi) ++b;
+  while (b >= 0 && pix_to_ndc(b, Sf) > hi) --b;
+  ilo = a;
+  ihi = b;
 }
 
 __global__ void __launch_bounds__(128) sil_setup_kernel(const float* __restrict__ verts, const float* __restrict__ K, const int* __restrict__ faces,
