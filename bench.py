@@ -334,6 +334,7 @@ def run_ours(args, rank, world, local_rank):
             configs["C2"] = L.config_c2(dev, peak, tf32_peak)
             configs["C3"] = L.config_c3(dev, peak)
             configs["api_autograd"] = L.autograd_api(dev)
+            configs["silhouette"] = L.silhouette_consumer(dev)
 
     if rank != 0:
         return

@@ -150,6 +150,39 @@ def autograd_api(dev, S=1024, reps=10):
             "what": "perspective_crop + MANOHead.r/.l autograd.Function drop-ins, per-call allocation + autograd, fwd+bwd"}
 
 
+def silhouette_consumer(dev, B=1024, reps=10):
+    """§8(f3) consumer: MANORenderer (soft silhouette of mano.v3d.cam, faces_per_pixel = 10) + fused L1 mask loss, fwd + bwd,
+    on the hand-sized synthetic mesh with MANO's counts (778 vertices, 1538 faces).  Issue-bound, not HBM-bound: the
+    algorithmic bytes (vertices in, one fp32 mask out, its gradient in, vertex gradients out) are reported for scale only."""
+    from hands_b200.losses import render_loss
+    from hands_b200.src.models.hands_light.renderer import MANORenderer
+    from hands_b200.synthetic import synthetic_silhouette_inputs
+
+    vc, faces, K = synthetic_silhouette_inputs(B, seed=0, img_res=IMG_RES)
+    r = MANORenderer({"img_res": IMG_RES}, faces_r=faces.numpy(), faces_l=faces.numpy()).to(dev)
+    v, meta = vc.to(dev), {"intrinsics": K.to(dev)}
+    gt = (torch.rand(B, 1, IMG_RES, IMG_RES, generator=torch.Generator().manual_seed(1)) > 0.5).float().to(dev)
+    valid = torch.ones(B, device=dev)
+    state = {}
+
+    def fwd():
+        state["x"] = v.requires_grad_(True)
+        state["m"] = r({"mano.v3d.cam.r": state["x"]}, meta, is_right=True)["mask"]
+
+    def full():
+        fwd()
+        render_loss(state["m"], gt, valid).backward()
+        state["x"].grad = None
+
+    t_f = cuda_time(fwd, reps, 3, dev)
+    t = cuda_time(full, reps, 3, dev)
+    cov = float((state["m"] > 0.5).float().mean())
+    abytes = B * (2 * 778 * 12 + 2 * IMG_RES * IMG_RES * 4)
+    return {"meshes": B, "fwd_ms": t_f * 1e3, "fwd_bwd_ms": t * 1e3, "meshes_per_s": B / t, "coverage": cov,
+            "algorithmic_gbytes_per_s": abytes / t / 1e9,
+            "what": "MANORenderer soft silhouette (778 verts, 1538 faces, 224^2, 10 faces/pixel) + L1 mask loss, fwd+bwd"}
+
+
 # ---- CPU baselines ----------------------------------------------------------------------------------------------------
 class CpuReferenceStep:
     """Reference torch CPU path for the C4 step: PCL (grid_sample + interpolate per crop, as the reference closure does) +
