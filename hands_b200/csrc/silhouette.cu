@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
     const float fx0 = pn[fc], fx1 = pn[fc + 7], fy0 = pn[fr], fy1 = pn[fr + 3];
     float qz[SIL_K], qd[SIL_K];
 #pragma unroll
-    for (int k = 0; k < SIL_K; ++k) { qz[k] = INFINITY; qd[k] = 1.0f; }   // qd = 1 - probability of the fragment
+    for (int k = 0; k < SIL_K; ++k) { qz[k] = INFINITY; qd[k] = 0.0f; }
     for (int base = 0; base < nb; base += 32) {
       // 32 faces of the band list against the footprint at once; the survivors are visited in list (= face) order
       const int j = base + lane;
@@ -256,9 +256,8 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
         const SilFace f = load_face(R + __shfl_sync(0xffffffffu, fidx, src) * SIL_REC);
         SilHit h;
         if (!sil_eval(f, px, py, blur, h)) continue;
-        float z = h.pz;
+        float z = h.pz, sd = h.inside ? -h.dist : h.dist;
         if (z < qz[SIL_K - 1]) {   // sorted insertion; a tie stays behind the earlier face
-          float sd = __fsub_rn(1.0f, sil_prob(h.inside ? -h.dist : h.dist, inv_sigma));
 #pragma unroll
           for (int k = 0; k < SIL_K; ++k) {
             const bool sw = z < qz[k];
@@ -273,7 +272,8 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
     }
     float alpha = 1.0f;
 #pragma unroll
-    for (int k = 0; k < SIL_K; ++k) alpha = __fmul_rn(alpha, qd[k]);   // in depth order, as sigmoid_alpha_blend multiplies
+    for (int k = 0; k < SIL_K; ++k)   // in depth order, as sigmoid_alpha_blend multiplies
+      if (qz[k] < INFINITY) alpha = __fmul_rn(alpha, __fsub_rn(1.0f, sil_prob(qd[k], inv_sigma)));
     if (row < S && col < S) {
       const size_t o = ((size_t)b * S + row) * S + col;
       mask[o] = __fsub_rn(1.0f, alpha);

@@ -220,3 +220,58 @@ def test_abi_errors(dev):
     assert lib.hb_sil_fwd(h.handle, p(v), p(K), 2, 224, SIGMA, BLUR, p(m), p(ws), need, None) == 0
     torch.cuda.synchronize()
     assert float(m.abs().max()) == 0.0
+
+
+def test_head_to_silhouette_chain_gradients(dev):
+    """MANOHead -> mano.v3d.cam -> MANORenderer -> render_loss -> backward into (rotmat, shape, cam): the consumer chained to
+    the path as hands_light/model.py:413-420 + loss_arctic_sf.py:172-183 chain it, against the oracle head (torch autograd)
+    fed with the oracle silhouette's vertex gradient.  The MANO template is the hand-sized tube mesh (778 / 1538)."""
+    from hands_b200.losses import render_loss
+    from hands_b200.src.models.hands_light.renderer import MANORenderer
+    from hands_b200.src.nets.hand_heads.mano_head import MANOHead
+    from hands_b200.synthetic import synthetic_mano_buffers
+    from oracle import geometry_oracle as O
+
+    verts, faces = synthetic_tube_mesh()
+    head = MANOHead(True, 1000.0, 224.0, synthetic=True).to(dev)
+    with torch.no_grad():
+        head.mano.v_template.copy_(verts)
+    buf = synthetic_mano_buffers(True)
+    buf["v_template"] = verts.clone()
+    B = 2
+    g = torch.Generator().manual_seed(7)
+    aa = 0.15 * torch.randn(B, 16, 3, generator=g, dtype=torch.float64)
+    aa[:, 0] = torch.tensor([[0.3, -0.2, 1.0], [-0.5, 0.4, -0.8]], dtype=torch.float64)
+    rotmat = O.batch_rodrigues(aa.reshape(-1, 3)).reshape(B, 16, 3, 3)
+    betas = 0.5 * torch.randn(B, 10, generator=g, dtype=torch.float64)
+    cam = torch.tensor([[8.0, 0.02, -0.03], [7.0, -0.04, 0.01]], dtype=torch.float64)
+    K = torch.tensor([[700.0, 0, 112], [0, 700.0, 112], [0, 0, 1]], dtype=torch.float64).repeat(B, 1, 1)
+
+    # oracle chain in fp64
+    leaves = [t.clone().requires_grad_(True) for t in (rotmat, betas, cam)]
+    o = O.mano_head_forward(buf_to(buf, torch.float64), leaves[0], leaves[1], leaves[2], K, 224.0, 0.1)
+    v64 = o["v3d.cam"].detach().numpy()
+    m64, frags, _ = so.soft_silhouette(v64, faces.numpy(), K.numpy(), 224, dtype=np.float64, return_fragments=True)
+    assert (m64 > 0.5).sum() > B * 3000
+    well = np.stack([f[6] for f in frags])[:, None] > 1e-5
+    gt = (np.random.default_rng(3).random(m64.shape) > 0.5).astype(np.float64)
+    gl = np.sign(m64 - gt) * well / m64.size
+    g_v = so.soft_silhouette_backward(v64, faces.numpy(), K.numpy(), gl, 224)
+    o["v3d.cam"].backward(torch.from_numpy(g_v))
+    ref = [t.grad for t in leaves]
+
+    # CUDA chain
+    cl = [t.float().to(dev).requires_grad_(True) for t in (rotmat, betas, cam)]
+    out = head(cl[0], cl[1], cl[2], K.float().to(dev))
+    r = MANORenderer({"img_res": 224}, faces_r=faces.numpy(), faces_l=faces.numpy()).to(dev)
+    mask = r({"mano.v3d.cam.r": out["v3d.cam.r"]}, {"intrinsics": K.float().to(dev)}, is_right=True)["mask"]
+    tol_check("chain: silhouette of the head's vertices vs fp64 oracle, untied pixels (abs)", np.abs(mask.detach().cpu().numpy() - m64)[well].max(), 5e-5)
+    gt_dev = torch.where(torch.from_numpy(well).to(dev), torch.from_numpy(gt).float().to(dev), mask.detach())
+    render_loss(mask, gt_dev, torch.ones(B, device=dev)).backward()
+    for name, got, want in zip(("g_rotmat", "g_shape", "g_cam"), (t.grad for t in cl), ref):
+        assert float(want.abs().max()) > 0
+        tol_check(f"chain: {name} through head + silhouette + mask loss (rel to max)", float((got.double().cpu() - want).abs().max() / want.abs().max()), 5e-4)
+
+
+def buf_to(buf, dtype):
+    return {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in buf.items()}
