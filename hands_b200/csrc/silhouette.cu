@@ -214,17 +214,25 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
   const float Sf = (float)S, inv_sigma = 1.0f / sigma;
   for (int i = tid; i < S + 16; i += 256) pn[i] = pix_to_ndc(i, Sf);   // one IEEE division per entry instead of per pixel
 
+  __shared__ int s_cmin, s_cmax, s_next;
+  if (tid == 0) { s_cmin = S; s_cmax = 0; s_next = 0; }
+  __syncthreads();
+  int cmin = S, cmax = 0;   // column extent [cmin, cmax) of the band's faces: footprints outside it are empty
   const int nb = compact_ordered(F, [&](int i, int& val) {
-    const int rows = __float_as_int(__ldg(&R[i * SIL_REC + 4]).z);
+    const float4 e = __ldg(&R[i * SIL_REC + 4]);
+    const int rows = __float_as_int(e.z), cols = __float_as_int(e.y);
     val = i;
-    return (rows & 0xffff) < r0 + SIL_TILE && (rows >> 16) > r0;
+    const bool keep = (rows & 0xffff) < r0 + SIL_TILE && (rows >> 16) > r0 && (cols >> 16) > (cols & 0xffff);
+    if (keep) { cmin = min(cmin, cols & 0xffff); cmax = max(cmax, cols >> 16); }
+    return keep;
   }, blist, s_wc);
+  if (cmin < cmax) { atomicMin(&s_cmin, cmin); atomicMax(&s_cmax, cmax); }
+  __syncthreads();
+  cmin = s_cmin;
+  cmax = s_cmax;
 
   // Footprints of 8 columns x 4 rows (one warp each), handed out dynamically: the band's warps never wait for each other
   // (which warp renders a footprint does not change its pixels).
-  __shared__ int s_next;
-  if (tid == 0) s_next = 0;
-  __syncthreads();
   const int fcols = (S + 7) / 8, nfp = fcols * (SIL_TILE / 4);
   for (;;) {
     int fp = 0;
@@ -238,12 +246,13 @@ __global__ void __launch_bounds__(256) sil_raster_kernel(const float4* __restric
     float qz[SIL_K], qd[SIL_K];
 #pragma unroll
     for (int k = 0; k < SIL_K; ++k) { qz[k] = INFINITY; qd[k] = 0.0f; }
-    for (int base = 0; base < nb; base += 32) {
+    const int nscan = (fc < cmax && fc + 8 > cmin) ? nb : 0;
+    for (int base = 0; base < nscan; base += 32) {
       // 32 faces of the band list against the footprint at once; the survivors are visited in list (= face) order
       const int j = base + lane;
       int fidx = 0;
       bool hit = false;
-      if (j < nb) {
+      if (j < nscan) {
         fidx = blist[j];
         const float4 d = __ldg(R + fidx * SIL_REC + 3);
         const float yhi = __ldg(R + fidx * SIL_REC + 4).x;
