@@ -275,3 +275,24 @@ def test_head_to_silhouette_chain_gradients(dev):
 
 def buf_to(buf, dtype):
     return {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in buf.items()}
+
+
+@pytest.mark.parametrize("S", [100, 37])
+def test_image_sizes_that_are_no_multiple_of_the_tile(dev, S):
+    vc, faces, K = synthetic_silhouette_inputs(2, seed=4, img_res=S)
+    K = K.clone()
+    K[:, 0, 0] *= S / 224.0
+    K[:, 1, 1] *= S / 224.0
+    got = render(vc, faces, K, S, dev).cpu().numpy()
+    ref, frags, _ = so.soft_silhouette(vc.numpy(), faces.numpy(), K.numpy(), S, dtype=np.float32, return_fragments=True)
+    tied = (np.stack([f[5] for f in frags]) > 10) & (np.stack([f[6] for f in frags]) <= 1e-6)
+    assert got.shape == (2, 1, S, S) and (ref > 0.5).sum() > 50
+    tol_check(f"silhouette mask at img_res {S} (abs)", np.abs(got - ref)[~tied[:, None]].max(), 5e-5)
+    g = np.random.default_rng(S).normal(size=got.shape).astype(np.float32) * ~tied[:, None]
+    _, gv = render(vc, faces, K, S, dev, g)
+    _, frags64, _ = so.soft_silhouette(vc.numpy().astype(np.float64), faces.numpy(), K.numpy().astype(np.float64), S, dtype=np.float64, return_fragments=True)
+    well = np.stack([f[6] for f in frags64])[:, None] > 1e-5
+    g = g * well
+    _, gv = render(vc, faces, K, S, dev, g)
+    ref_g = so.soft_silhouette_backward(vc.numpy().astype(np.float64), faces.numpy(), K.numpy().astype(np.float64), g.astype(np.float64), S)
+    tol_check(f"silhouette g_verts at img_res {S} (rel to max)", np.abs(gv.cpu().numpy() - ref_g).max() / np.abs(ref_g).max(), 5e-4)
