@@ -43,5 +43,20 @@ for B in (5, 130):
     l3, l2, _ = keypoint_losses(o["j3d.cam.r"], o["j2d.norm.r"], torch.zeros(B, 21, 3, device=dev), torch.zeros(B, 21, 2, device=dev), torch.ones(B, 21, device=dev))
     lv = vector_loss(o["cam_t.wp.r"], torch.zeros(B, 3, device=dev), torch.ones(B, device=dev), None, pred2=cam)
     (l3 + l2 + lv).backward()
+# soft-silhouette consumer: two image sizes (one no multiple of the tile), a degenerate and an off-screen face, mask loss
+from hands_b200.losses import render_loss  # noqa: E402
+from hands_b200.src.models.hands_light.renderer import MANORenderer  # noqa: E402
+from hands_b200.synthetic import synthetic_silhouette_inputs  # noqa: E402
+
+for S in (224, 52):
+    vc, faces, K = synthetic_silhouette_inputs(2, seed=S, img_res=S)
+    K[:, 0, 0] *= S / 224.0
+    K[:, 1, 1] *= S / 224.0
+    vc[0, 5] = vc[0, 6]              # zero-area faces
+    vc[1, 700:] += 5.0               # part of the mesh far off screen
+    rdr = MANORenderer({"img_res": S}, faces_r=faces.numpy(), faces_l=faces.numpy()).to(dev)
+    v = vc.to(dev).requires_grad_(True)
+    m = rdr({"mano.v3d.cam.r": v}, {"intrinsics": K.to(dev)}, is_right=True)["mask"]
+    render_loss(m, torch.zeros_like(m), torch.ones(2, device=dev)).backward()
 torch.cuda.synchronize()
 print("sanitize_small: done")
