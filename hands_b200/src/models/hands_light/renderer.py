@@ -29,11 +29,20 @@ class DiffRenderer(nn.Module):
         self._handles = {}
 
     def _handle(self, faces, n_verts, device):
-        key = (faces.data_ptr() if isinstance(faces, torch.Tensor) else id(faces), int(n_verts), str(device))
-        h = self._handles.get(key)
-        if h is None:
-            h = self._handles[key] = SilhouetteHandle(faces, n_verts, device)
-        return h
+        """hb_sil* for this face table on `device`; rebuilt when the table is replaced or edited in place."""
+        faces = torch.as_tensor(faces)
+        key = (int(n_verts), device.type, device.index if device.index is not None else torch.cuda.current_device())
+        stamp = (faces.data_ptr(), faces._version, tuple(faces.shape))
+        hit = self._handles.get(key)
+        if hit is None or hit[0] != stamp:
+            hit = self._handles[key] = (stamp, SilhouetteHandle(faces, n_verts, device))
+        return hit[1]
+
+    # the handle cache holds ctypes pointers to device memory: never copied or pickled with the module
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"] = {}
+        return state
 
     def forward(self, verts_cam, faces, K):
         """verts_cam (B,V,3) camera space, faces (F,3) shared by the batch, K (B,3,3) pixel intrinsics."""

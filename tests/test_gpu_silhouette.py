@@ -296,3 +296,25 @@ def test_image_sizes_that_are_no_multiple_of_the_tile(dev, S):
     _, gv = render(vc, faces, K, S, dev, g)
     ref_g = so.soft_silhouette_backward(vc.numpy().astype(np.float64), faces.numpy(), K.numpy().astype(np.float64), g.astype(np.float64), S)
     tol_check(f"silhouette g_verts at img_res {S} (rel to max)", np.abs(gv.cpu().numpy() - ref_g).max() / np.abs(ref_g).max(), 5e-4)
+
+
+def test_renderer_module_copies_and_face_edits(dev):
+    """The module can be deep-copied / pickled after a forward (its handle cache holds raw pointers and is dropped), and an
+    in-place edit of the face table is picked up."""
+    import copy
+    import pickle
+
+    from hands_b200.src.models.hands_light.renderer import MANORenderer
+
+    vc, faces, K = synthetic_silhouette_inputs(1, seed=5)
+    r = MANORenderer({"img_res": 224}, faces_r=faces.numpy(), faces_l=faces.numpy()).to(dev)
+    meta = {"intrinsics": K.to(dev)}
+    m0 = r({"mano.v3d.cam.r": vc.to(dev)}, meta)["mask"]
+    r2 = copy.deepcopy(r)
+    r3 = pickle.loads(pickle.dumps(r))
+    assert torch.equal(r2({"mano.v3d.cam.r": vc.to(dev)}, meta)["mask"], m0)
+    assert torch.equal(r3.to(dev)({"mano.v3d.cam.r": vc.to(dev)}, meta)["mask"], m0)
+    with torch.no_grad():
+        r.mano_faces_r[: faces.shape[0] // 2] = r.mano_faces_r[0]        # half of the mesh collapses onto one face
+    m1 = r({"mano.v3d.cam.r": vc.to(dev)}, meta)["mask"]
+    assert float(m1.sum()) < 0.8 * float(m0.sum())
