@@ -261,7 +261,8 @@ int hb_sil_destroy(hb_sil* h);
 /* Caller-owned scratch shared by forward and backward: face records (80 B/face), (alpha, depth threshold) per pixel,
  *   per-face corner gradients.  hb_sil_bwd must see the workspace exactly as hb_sil_fwd of the same inputs left it. */
 size_t hb_sil_workspace_bytes(const hb_sil* h, int n_meshes, int img_res);
-/* verts_cam (n_meshes, n_verts, 3) camera space; K (n_meshes,3,3) pixel intrinsics; mask (n_meshes,1,img_res,img_res). */
+/* verts_cam (n_meshes, n_verts, 3) camera space; K (n_meshes,3,3) pixel intrinsics; mask (n_meshes,1,img_res,img_res).
+ *   At most 65535 meshes per call (HB_E_UNSUPPORTED beyond; split the batch), img_res <= 4096. */
 int hb_sil_fwd(const hb_sil* h, const float* verts_cam, const float* K, int n_meshes, int img_res, float sigma,
                float blur_radius, float* mask, void* workspace, size_t workspace_bytes, void* stream);
 /* g_mask (n_meshes,1,img_res,img_res) -> g_verts (n_meshes,n_verts,3), every element written once (no atomics). */
