@@ -1131,7 +1131,10 @@ constexpr int PCL_RECS = 4;            // crop records cached in shared memory p
 
 template <int C, int RT>
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
-                                                                  int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img) {
+                                                                  int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img,
+                                                                  const int* __restrict__ list) {
+  // list == nullptr: blockIdx.y is the image inside the chunk; otherwise list[0] images list[1..] (the ones the scatter
+  // kernel left) are walked by gridDim.y CTA rows
   const int R = RT ? RT : R_arg;
   extern __shared__ __align__(16) uint8_t img_sm[];
   float4* ent_g = reinterpret_cast<float4*>(img_sm);                                   // [PCL_REG] staged region: gradient ...
@@ -1144,8 +1147,12 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   __shared__ int box[4];
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
-  const int im = img_base + blockIdx.y;
   const int lx = threadIdx.x & 31, lyb = threadIdx.x >> 5;  // 32 x 8 threads, 4 adjacent rows each
+  __shared__ float recs[PCL_RECS * PF];
+  const int n_list = list ? __ldg(list) : (int)gridDim.y;
+  for (int le = blockIdx.y; le < n_list; le += gridDim.y) {
+  const int im = list ? __ldg(list + 1 + le) : img_base + (int)blockIdx.y;
+  __syncthreads();   // the previous image's readers are done with recs
   float acc[4][C];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -1153,7 +1160,6 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     for (int ch = 0; ch < C; ++ch) acc[r][ch] = 0.f;
   // the records of the image's (first PCL_RECS) crops are fetched once, all fields in flight together, instead of a chain
   // of dependent global loads per crop
-  __shared__ float recs[PCL_RECS * PF];
   for (int e = threadIdx.x; e < min(crops_per_img, PCL_RECS) * PF; e += PCL_THREADS) recs[e] = __ldg(params + (size_t)im * crops_per_img * PF + e);
   __syncthreads();
   for (int k = 0; k < crops_per_img; ++k) {
@@ -1347,17 +1353,318 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) __stcs(op + ch * R * R, acc[r][ch]);
   }
+  }
+}
+
+
+// ---- transposed grid_sample, scatter form ----------------------------------------------------------
+// The crop's samples are about one source pixel apart (s = the box side), so binning them into per-pixel lists (the
+// gather kernel above) spends ten warp instructions per sample on bookkeeping.  Here the samples are scattered instead,
+// WITHOUT atomics and in a fixed order, into a rolling window of source rows in shared memory:
+//   * one CTA per image; the window [base, base + 32) of source rows moves down the image once, every row of g_img is
+//     written exactly once when no remaining intermediate row of any crop can reach it (rows no crop touches: zeros);
+//   * per window position each crop of the image takes a band of its next (warps x NP) intermediate rows that fit;
+//     a warp owns a whole intermediate row; lanes are consecutive samples of it, 31 new ones per strip (lane 0 repeats the
+//     previous strip's last sample as a provider).  x grows by more than half a pixel per sample (checked by the setup
+//     kernel, slot 26 of the record), so the left pixel columns of a strip's samples are distinct unless two neighbours
+//     share one (ballot -> four sub-phases for that strip).  A sample's right-column contribution is handed to its
+//     neighbour through shuffles when that neighbour's left column is the same pixel column in the same pixel row;
+//     otherwise (pixel-row crossing, skipped column, row end) the lane adds it itself after a __syncwarp;
+//   * rows NP apart touch disjoint pixels wherever they come within two columns of each other (setup kernel's bound), so
+//     the warps run rows j, j+NP, j+2NP, ... concurrently and a block barrier separates the NP phases of a band;
+//   * the gradients of a warp's next row (or next 124 samples of a long row) are loaded while it works on the current ones.
+// Every pixel's sum has a fixed order (window position, crop, phase, row, strip, sub-phase): bit-reproducible and
+// independent of the sharding.  Images with a crop the bounds reject are listed by pcl_fallback_list_kernel and taken by
+// the gather kernel.
+constexpr int PCL_SC_WARPS = 8;
+constexpr int PCL_SC_THREADS = 32 * PCL_SC_WARPS;
+constexpr int PCL_SC_PAD = 4;            // window columns left and right of the image (16-byte aligned image rows)
+constexpr int PCL_SC_SPT = 4;            // strips (31 samples) per load group
+constexpr int PCL_SC_MAXC = 8;           // most crops per image (more: gather kernel)
+
+struct ScRow { float lo, hi; };
+
+// y range of intermediate row j: along a row y is a Moebius function of u, so its extremes are at the two ends
+__device__ __forceinline__ ScRow sc_row_y(const Crop& c, int j) {
+  const float v = lin01(c, j);
+  const float Y0 = fmaf(c.P[4], v, c.P[5]), Z0 = fmaf(c.P[7], v, c.P[8]) + 1e-8f;
+  const float ya = __fdividef(Y0, Z0) - 0.5f, yb = __fdividef(Y0 + c.P[3], Z0 + c.P[6]) - 0.5f;
+  ScRow r;
+  r.lo = fminf(ya, yb); r.hi = fmaxf(ya, yb);
+  return r;
+}
+
+template <int RT>
+__global__ void __launch_bounds__(PCL_SC_THREADS, 2) pcl_bwd_scatter_kernel(const float* __restrict__ params, const float* __restrict__ ws,
+                                                                          int img_base, int crops_per_img, float* __restrict__ g_img) {
+  constexpr int R = RT, W = R + 2 * PCL_SC_PAD, PLANE = PCL_SC_H * W, HM = PCL_SC_H - 1, R4 = R / 4, RW = 3 * R4;
+  static_assert(PCL_SC_THREADS > RW && PCL_SC_THREADS < 2 * RW, "incremental index split of the row loops");
+  extern __shared__ __align__(16) float win[];   // [3][PCL_SC_H][W]
+  __shared__ int s_j[PCL_SC_MAXC];               // next intermediate row of each crop
+  const int im = img_base + blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float* rec0 = params + (size_t)im * crops_per_img * PF;
+  for (int k = 0; k < crops_per_img; ++k)
+    if (__float_as_int(__ldg(rec0 + k * PF + 26)) == 0) return;   // the gather kernel takes this image
+  for (int idx = tid; idx < 3 * PLANE / 4; idx += PCL_SC_THREADS) reinterpret_cast<float4*>(win)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < PCL_SC_MAXC) s_j[tid] = 0;
+  __syncthreads();
+  float* gout = g_img + (size_t)im * 3 * R * R;
+  // image rows [r0, r1) are zero
+  auto zero_rows = [&](int r0, int r1) {
+    const int total = (r1 - r0) * RW;
+    int rr = tid / RW, rem = tid - rr * RW;
+    for (int idx = tid; idx < total; idx += PCL_SC_THREADS) {
+      const int ch = rem >= 2 * R4 ? 2 : (rem >= R4 ? 1 : 0), x4 = rem - ch * R4;
+      __stcs(reinterpret_cast<float4*>(gout + ((size_t)ch * R + r0 + rr) * R) + x4, make_float4(0.f, 0.f, 0.f, 0.f));
+      rem += PCL_SC_THREADS - RW; rr += 1;
+      if (rem >= RW) { rem -= RW; rr += 1; }
+    }
+  };
+  // smallest pixel row an unfinished crop can still touch (R + 1: all crops done)
+  // (lane k evaluates crop k; one warp reduction instead of a loop every thread repeats)
+  auto next_base = [&]() {
+    int nb = R + 1;
+    if (lane < crops_per_img) {
+      const Crop c = load_crop(rec0 + lane * PF);
+      const int j = s_j[lane];
+      if (j < c.s) nb = min(max((int)floorf(sc_row_y(c, j).lo - 0.05f), -1), R);
+    }
+    return __reduce_min_sync(0xffffffffu, nb);
+  };
+  int base = next_base();
+  zero_rows(0, min(base, R));
+  for (int step = 0; step < 8 * R && base <= R; ++step) {   // (the cap only guards against a hang; every step retires rows or takes a band)
+    for (int k = 0; k < crops_per_img; ++k) {
+      const float* rec = rec0 + k * PF;
+      const Crop c = load_crop(rec);
+      const int s = c.s, j = s_j[k];
+      if (j >= s) continue;
+      const int NP = __float_as_int(__ldg(rec + 26));
+      // band: as many rows (one group of NP per warp) as the window holds
+      // (lane l tries PCL_SC_WARPS - l warps; the first lane that fits wins)
+      int nw = 0, nb = 0;
+      {
+        const int tw = PCL_SC_WARPS - (lane & (PCL_SC_WARPS - 1));
+        const int n = min(tw * NP, s - j);
+        const int top = min((int)floorf(sc_row_y(c, j + n - 1).hi + 0.05f) + 1, R);
+        const unsigned fits = __ballot_sync(0xffffffffu, top - base <= HM) & ((1u << PCL_SC_WARPS) - 1u);
+        if (fits) { nw = PCL_SC_WARPS - (__ffs(fits) - 1); nb = min(nw * NP, s - j); }
+      }
+      if (nb == 0) continue;   // block-uniform
+      const float4* G = reinterpret_cast<const float4*>(ws + __float_as_int(__ldg(rec + 21)));
+      const int row0 = j + wid * NP;
+      const bool wact = wid < nw;
+      // next band of this crop (after the other crops' bands): its gradients into L2 now
+      {
+        const char* nx = reinterpret_cast<const char*>(G + (size_t)(j + nb) * s);
+        const int nbytes = min(PCL_SC_WARPS * NP, s - j - nb) * s * 16;
+        for (int o = tid * 128; o < nbytes; o += PCL_SC_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+      }
+      const int sm1 = s - 1, half = s >> 1;
+      const float fsm1 = (float)sm1;
+      // (indices are clamped instead of predicated: a lane outside the row reads a neighbour's value and never uses it)
+      auto load_task = [&](int row, int t0, float4 (&g)[PCL_SC_SPT]) {
+        const float4* Grow = G + (size_t)min(row, sm1) * s;
+#pragma unroll
+        for (int q = 0; q < PCL_SC_SPT; ++q) g[q] = __ldcs(Grow + min(max(t0 + 31 * q - 1 + lane, 0), sm1));
+      };
+      float4 gq[PCL_SC_SPT], gn[PCL_SC_SPT];
+      load_task(row0, 0, gn);
+      for (int p = 0; p < NP; ++p) {
+        const int row = row0 + p;
+        const bool ract = wact && row < j + nb;
+        const float v = lin01(c, min(row, sm1));
+        for (int t0 = 0; t0 < s; t0 += 31 * PCL_SC_SPT) {
+#pragma unroll
+          for (int q = 0; q < PCL_SC_SPT; ++q) gq[q] = gn[q];
+          if (t0 + 31 * PCL_SC_SPT < s) load_task(row, t0 + 31 * PCL_SC_SPT, gn);
+          else if (p + 1 < NP) load_task(row + 1, 0, gn);
+          if (!ract) continue;   // warp-uniform
+#pragma unroll
+          for (int qp = 0; qp < PCL_SC_SPT; qp += 2) {
+            if (t0 + 31 * qp >= s) break;   // warp-uniform
+            // two strips at once (independent instruction chains): their samples' left columns are all distinct unless
+            // two neighbours share one (then: one strip after the other, four sub-phases each)
+            float ax[2], ay[2], gv[2][3];
+            float* at[2];
+            float* ab[2];
+            int key[2];
+            bool ok[2], dup[2], fwd_in[2], defer[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = t0 + 31 * (qp + h) - 1 + lane;
+              const float fi = (float)i;
+              const float u = (i < half) ? __fmul_rn(c.step, fi) : fmaf(-c.step, fsm1 - fi, 1.0f);   // lin01 (s >= 2 here)
+              // same expression as the gather kernel's binning pass (the two forms then differ by summation order only)
+              const float X = fmaf(c.P[1], v, c.P[0] * u) + c.P[2];
+              const float Y = fmaf(c.P[4], v, c.P[3] * u) + c.P[5];
+              const float Z = fmaf(c.P[7], v, c.P[6] * u) + c.P[8];
+              const float iz = __fdividef(1.0f, 1e-8f + Z);
+              const float x = X * iz - 0.5f, y = Y * iz - 0.5f;
+              const float fxf = floorf(x), fyf = floorf(y);
+              ax[h] = x - fxf; ay[h] = y - fyf;
+              // floor in [-1, R-1] on both axes  <=>  |floor - (R/2 - 1)| <= R/2   (NaN: false)
+              ok[h] = (unsigned)i < (unsigned)s && (h == 0 || t0 + 31 * (qp + 1) < s) &&
+                      fabsf(fxf - (float)(R / 2 - 1)) <= (float)(R / 2) && fabsf(fyf - (float)(R / 2 - 1)) <= (float)(R / 2);
+              const int fx = (int)fxf, fy = (int)fyf;
+              key[h] = ok[h] ? ((fy + 1) << 10) + fx + 1 : -5;
+              defer[h] = lane == 31 && i < sm1;   // the next strip's lane 0 handles this sample's right column
+              // (lanes that own nothing point at pad columns nobody reads: the left-column update below needs no branch)
+              const bool own = ok[h] && lane > 0;
+              at[h] = win + (own || ok[h] ? (fy & HM) * W + fx + PCL_SC_PAD : lane & 3);
+              ab[h] = win + (own || ok[h] ? ((fy + 1) & HM) * W + fx + PCL_SC_PAD : lane & 3);
+              const float4 g = gq[qp + h];
+              gv[h][0] = g.x; gv[h][1] = g.y; gv[h][2] = g.z;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              int nkey = __shfl_up_sync(0xffffffffu, key[h], 1);
+              if (lane == 0) nkey = -9;
+              fwd_in[h] = ok[h] && nkey + 1 == key[h];                            // neighbour's right column is my left column, same pixel row
+              dup[h] = ok[h] && nkey >= 0 && ((nkey ^ key[h]) & 1023) == 0;        // neighbour shares my left column
+            }
+            const unsigned m_dup = __ballot_sync(0xffffffffu, dup[0] || dup[1]);
+            if (m_dup == 0) {
+              bool needB[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const unsigned m_fwd = __ballot_sync(0xffffffffu, fwd_in[h]);
+                const float n_ax = __shfl_up_sync(0xffffffffu, ax[h], 1), n_ay = __shfl_up_sync(0xffffffffu, ay[h], 1);
+                float ng[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) ng[ch] = __shfl_up_sync(0xffffffffu, gv[h][ch], 1);
+                const float nwx = fwd_in[h] ? n_ax : 0.0f;
+                const float bx = 1.0f - ax[h], by = 1.0f - ay[h];
+                const float wlt = bx * by, wlb = bx * ay[h], nt = nwx * (1.0f - n_ay), nbm = nwx * n_ay;
+                {
+                  // lane 0 of a later strip is a provider (its sample's left column was the previous strip's), a lane that is
+                  // not ok points at a pad column
+                  float* pt = (ok[h] && lane == 0) ? win + (lane & 3) : at[h];
+                  float* pb = (ok[h] && lane == 0) ? win + (lane & 3) : ab[h];
+#pragma unroll
+                  for (int ch = 0; ch < 3; ++ch) {
+                    pt[ch * PLANE] = fmaf(wlt, gv[h][ch], fmaf(nt, ng[ch], pt[ch * PLANE]));
+                    pb[ch * PLANE] = fmaf(wlb, gv[h][ch], fmaf(nbm, ng[ch], pb[ch * PLANE]));
+                  }
+                }
+                const bool sent = lane < 31 && ((m_fwd >> (lane + 1)) & 1u);   // my right column went to lane + 1
+                needB[h] = ok[h] && !sent && !defer[h];
+              }
+              __syncwarp();
+              if (__ballot_sync(0xffffffffu, needB[0] || needB[1])) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (needB[h]) {
+                    const float wrt = ax[h] * (1.0f - ay[h]), wrb = ax[h] * ay[h];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                      at[h][ch * PLANE + 1] = fmaf(wrt, gv[h][ch], at[h][ch * PLANE + 1]);
+                      ab[h][ch * PLANE + 1] = fmaf(wrb, gv[h][ch], ab[h][ch * PLANE + 1]);
+                    }
+                  }
+                }
+                __syncwarp();
+              }
+            } else {
+              // two neighbours share a pixel column somewhere in these strips: strip by strip, first-of-a-column lanes,
+              // then the others; left columns, then right columns (no hand-over)
+              for (int h = 0; h < 2; ++h) {
+                const float bx = 1.0f - ax[h], by = 1.0f - ay[h];
+                for (int sub = 0; sub < 4; ++sub) {
+                  const bool mine = ok[h] && (dup[h] == (sub >= 2));
+                  if ((sub & 1) == 0) {
+                    if (mine && lane > 0) {
+                      const float wlt = bx * by, wlb = bx * ay[h];
+#pragma unroll
+                      for (int ch = 0; ch < 3; ++ch) {
+                        at[h][ch * PLANE] = fmaf(wlt, gv[h][ch], at[h][ch * PLANE]);
+                        ab[h][ch * PLANE] = fmaf(wlb, gv[h][ch], ab[h][ch * PLANE]);
+                      }
+                    }
+                  } else if (mine && !defer[h]) {
+                    const float wrt = ax[h] * by, wrb = ax[h] * ay[h];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                      at[h][ch * PLANE + 1] = fmaf(wrt, gv[h][ch], at[h][ch * PLANE + 1]);
+                      ab[h][ch * PLANE + 1] = fmaf(wrb, gv[h][ch], ab[h][ch * PLANE + 1]);
+                    }
+                  }
+                  __syncwarp();
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (p == 0 && tid == 0) s_j[k] = j + nb;   // every thread read s_j[k] before the barrier above; seen after the next one (NP >= 3)
+      }
+    }
+    // rows below nbs are final: no remaining intermediate row of any crop reaches them (y grows from row to row)
+    const int nbs = max(next_base(), base);
+    {
+      const int nrow = min(nbs, base + PCL_SC_H) - base;
+      if (tid < RW) {   // thread = (channel, four columns), walking down the retired rows
+        const int ch = tid / R4, x4 = tid - ch * R4;
+        float* wcol = win + ch * PLANE + PCL_SC_PAD + 4 * x4;
+        float* gcol = gout + (size_t)ch * R * R + 4 * x4;
+#pragma unroll 4
+        for (int rr = 0; rr < nrow; ++rr) {
+          const int Y = base + rr;
+          float4* wp = reinterpret_cast<float4*>(wcol + (Y & HM) * W);
+          const float4 val = *wp;
+          *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (Y >= 0 && Y < R) __stcs(reinterpret_cast<float4*>(gcol + Y * R), val);
+        }
+      }
+      if (nbs > base + PCL_SC_H) zero_rows(min(base + PCL_SC_H, R), min(nbs, R));
+    }
+    __syncthreads();
+    base = nbs;
+  }
+}
+
+// images of a chunk the scatter kernel leaves to the gather kernel (a crop with record slot 26 == 0), in image order
+__global__ void __launch_bounds__(1024) pcl_fallback_list_kernel(const float* __restrict__ params, int img_base, int n_imgs, int crops_per_img,
+                                                                int* __restrict__ list /* [0] = count, [1..] = image indices */) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n_imgs; b0 += 1024) {
+    const int e = b0 + threadIdx.x;
+    int flag = 0;
+    if (e < n_imgs)
+      for (int k = 0; k < crops_per_img; ++k) flag |= __float_as_int(__ldg(params + (size_t)((img_base + e) * crops_per_img + k) * PF + 26)) == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_tot[wid] = __popc(m);
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < wid; ++w) before += warp_tot[w];
+    if (flag) list[1 + before + __popc(m & ((1u << lane) - 1u))] = img_base + e;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + __popc(m);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) list[0] = carry;
 }
 
 }  // namespace hb
 
 using namespace hb;
 
+static int g_pcl_scatter = -1;   // -1: not decided yet (env HB_PCL_SCATTER, default 0: measured 527 vs 399 us per 1024 images)
+static int pcl_scatter() {
+  if (g_pcl_scatter < 0) { const char* e = getenv("HB_PCL_SCATTER"); g_pcl_scatter = (e && e[0] == '1') ? 1 : 0; }
+  return g_pcl_scatter;
+}
 static int g_pcl_exact = -1;   // -1: not decided yet (env HB_PCL_EXACT, default 0 = fast forward)
 static int pcl_exact() {
   if (g_pcl_exact < 0) { const char* e = getenv("HB_PCL_EXACT"); g_pcl_exact = (e && e[0] == '1') ? 1 : 0; }
   return g_pcl_exact;
 }
+extern "C" int hb_pcl_set_scatter(int on) { const int prev = pcl_scatter(); g_pcl_scatter = on ? 1 : 0; return prev; }
 extern "C" int hb_pcl_set_exact(int on) { const int prev = pcl_exact(); g_pcl_exact = on ? 1 : 0; return prev; }
 
 template <int C, typename SrcT>
@@ -1446,9 +1753,11 @@ extern "C" int hb_pcl_fwd_u8(const uint8_t* img, const float* mean_host, const f
 // for boxes of side U{56..168}).
 static const int kPclChunkImgs = 4096;   // measured per 8192-image step: 512 -> 6.28 ms, 1024 -> 6.11, 2048 -> 6.05, 4096 -> 6.01, 8192 -> 6.00 (1.6 MB of workspace per image)
 
-static size_t pcl_ws_bytes_per_img(int crops_per_img, int img_res) {
+static size_t pcl_ws_g_bytes_per_img(int crops_per_img, int img_res) {
   return sizeof(float) * (size_t)crops_per_img * (((size_t)PCL_WS_FLOATS_PER_PX * img_res * img_res + 3) & ~(size_t)3);
 }
+// + 16 bytes per image behind the chunk's gradients: the list of images the scatter kernel leaves to the gather kernel
+static size_t pcl_ws_bytes_per_img(int crops_per_img, int img_res) { return pcl_ws_g_bytes_per_img(crops_per_img, img_res) + 16; }
 
 extern "C" size_t hb_pcl_bwd_workspace_bytes(int n_crops, int crops_per_img, int C, int img_res) {
   (void)C;
@@ -1485,6 +1794,11 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const bool mid4 = want_mid4 && use_tma && smem_mid4 <= 200 * 1024;
   auto mid4_kernel = (R == 224) ? pcl_bwd_mid4_kernel<C, 224> : pcl_bwd_mid4_kernel<C, 0>;
   if (mid4) HB_CUDA(cudaFuncSetAttribute(mid4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid4));
+  // scatter form of the transposed grid_sample (C == 3, R == 224); HB_PCL_SCATTER=0 keeps the gather kernel for every image
+  const bool scatter = pcl_scatter() && C == 3 && R == 224 && crops_per_img <= PCL_SC_MAXC;
+  const size_t smem_sc = sizeof(float) * 3 * PCL_SC_H * (size_t)(R + 2 * PCL_SC_PAD);
+  if (scatter) HB_CUDA(cudaFuncSetAttribute(pcl_bwd_scatter_kernel<224>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+  int* fb_list = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + (size_t)chunk_imgs * pcl_ws_g_bytes_per_img(crops_per_img, R));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
   const size_t smem_img = (size_t)PCL_REG * 24 + PCL_CNT_BYTES + PCL_LST_BYTES + 128 * sizeof(float);
   auto img_kernel = (R == 224) ? pcl_bwd_img_kernel<C, 224> : pcl_bwd_img_kernel<C, 0>;
@@ -1501,8 +1815,16 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
       if (rc) return rc;
     }
     dim3 g2(tiles, nim);
-    if (stages & 2) {
-      img_kernel<<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img);
+    if ((stages & 2) && scatter) {
+      pcl_fallback_list_kernel<<<1, 1024, 0, st>>>(params, im0, nim, crops_per_img, fb_list);
+      pcl_bwd_scatter_kernel<224><<<nim, PCL_SC_THREADS, smem_sc, st>>>(params, ws, im0, crops_per_img, g_img);
+      dim3 g3(tiles, nim < 8 ? nim : 8);   // the listed images (usually none) walked by 8 CTA rows
+      img_kernel<<<g3, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, fb_list);
+      g_launches += 3;
+      rc = check_launch("pcl_bwd_scatter_kernel");
+      if (rc) return rc;
+    } else if (stages & 2) {
+      img_kernel<<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, nullptr);
       g_launches++;
       rc = check_launch("pcl_bwd_img_kernel");
       if (rc) return rc;

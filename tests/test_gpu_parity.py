@@ -774,3 +774,55 @@ def test_backward_reusing_forward_workspace_is_bit_identical(heads, dev):
     second = torch.autograd.grad(loss, (r, b, c))
     for a, bb in zip(first, second):
         assert torch.equal(a, bb)
+
+
+def _pcl_grad(dev, img, bbox, K, w, cpi, scatter):
+    from hands_b200 import _lib
+    from hands_b200.pcl import perspective_crop
+
+    prev = _lib.load().hb_pcl_set_scatter(scatter)
+    try:
+        x = img.to(dev).requires_grad_(True)
+        crop, _ = perspective_crop(x, bbox.to(dev), K.to(dev), img_res=224, crops_per_img=cpi)
+        (g,) = torch.autograd.grad(crop, x, grad_outputs=w.to(dev))
+        return g
+    finally:
+        _lib.load().hb_pcl_set_scatter(prev)
+
+
+@pytest.mark.parametrize("fmin,fmax,cpi", [(300.0, 1500.0, 2), (110.0, 200.0, 2), (60.0, 110.0, 3), (2000.0, 9000.0, 1)])
+def test_pcl_backward_scatter_form(dev, fmin, fmax, cpi):
+    """The scatter form of the transposed grid_sample (default for 3x224x224) against the oracle's autograd and against the
+    gather form, from mild to extreme perspective (short focal lengths: rows drift over many pixel rows, samples closer than
+    a pixel, narrow bands, images the setup kernel's bounds hand to the gather kernel), with boxes that leave the image
+    corner regions empty, overlap each other and touch the border.  Bit-reproducible run to run."""
+    B = 12
+    n = B * cpi
+    img, bbox, K = synthetic_pcl_inputs(n, seed=int(fmin), img_res=224, smin=40, smax=224)
+    img = img[:B].contiguous()
+    g = torch.Generator().manual_seed(int(fmax))
+    f = fmin + (fmax - fmin) * torch.rand(n, generator=g)
+    K[:, 0, 0] = f
+    K[:, 1, 1] = f * (0.9 + 0.2 * torch.rand(n, generator=g))
+    K[:, 0, 2] += 30 * torch.randn(n, generator=g)
+    bbox[0] = torch.tensor([0, 0, 223, 223])
+    bbox[1] = torch.tensor([150, 160, 223, 223])
+    bbox[2] = torch.tensor([0, 0, 40, 223])
+    w = torch.randn(n, 3, 224, 224, generator=g)
+    gs = _pcl_grad(dev, img, bbox, K, w, cpi, 1)
+    gg = _pcl_grad(dev, img, bbox, K, w, cpi, 0)
+    assert torch.equal(gs, _pcl_grad(dev, img, bbox, K, w, cpi, 1))
+    # (under extreme perspective the gather form's own fall-back path evaluates the sample positions with another reciprocal)
+    assert rel(gs, gg.cpu()) <= (2e-6 if fmin >= 300.0 else 2e-5)
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        xr = img.clone().requires_grad_(True)
+        ref_crop, _ = O.perspective_crop(xr.repeat_interleave(cpi, dim=0), bbox, K, 224)
+        (ref_g,) = torch.autograd.grad(ref_crop, xr, grad_outputs=w)
+    finally:
+        torch.set_num_threads(nt)
+    assert rel(gs, ref_g) <= 1e-4
+    # per-image check as well (one bad image must not hide behind the batch's largest value)
+    for b in range(B):
+        assert rel(gs[b], ref_g[b]) <= 1e-4, b
