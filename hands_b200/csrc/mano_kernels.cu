@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 3) mano_skin_fwd_kernel(Mano
   if (USE_VP) {
     // v_posed comes from the tensor-core kernel: [hand][k][800] coordinate-major, coalesced over vertices
 #pragma unroll 4
-    for (int h = 0; h < HBF; ++h) {
+    for (int h = (int)blockIdx.z * (HBF / (int)gridDim.z); h < ((int)blockIdx.z + 1) * (HBF / (int)gridDim.z); ++h) {
       const int b = min(b0 + h, B - 1);
       const float* src = vp + (size_t)b * (3 * VP) + v;
       Xs[h * XS + 3 * tid + 0] = __ldg(src); Xs[h * XS + 3 * tid + 1] = __ldg(src + VP); Xs[h * XS + 3 * tid + 2] = __ldg(src + 2 * VP);
@@ -315,8 +315,10 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 3) mano_skin_fwd_kernel(Mano
 #pragma unroll
   for (int j = 0; j < NJ; ++j) w[j] = __ldg(c.Wt + j * VP + v);
   const int tip = v < NV ? tip_slot(c, v) : -1;
-  const int nh = min(HBF, B - b0);
-  for (int h = 0; h < nh; ++h) {
+  // small batches: the group's 16 hands are split over gridDim.z CTAs (more CTAs in flight, shorter serial chain)
+  const int hz0 = (int)blockIdx.z * (HBF / (int)gridDim.z);
+  const int nh = min(hz0 + HBF / (int)gridDim.z, B - b0);
+  for (int h = hz0; h < nh; ++h) {
     float T[12];
     blend_transforms(As + h * AS, w, T);
     float* xs = Xs + h * XS + 3 * tid;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 3) mano_skin_fwd_kernel(Mano
   __syncthreads();
   // coalesced float2 stores: this slice owns floats [slice*480, slice*480 + nvalid) of each hand's 2334
   const int nvalid = min(VPB, NV - slice * VPB) * 3;
-  for (int h = 0; h < nh; ++h) {
+  for (int h = hz0; h < nh; ++h) {
     const float* of = Os + h * 8;
     const size_t base = (size_t)(b0 + h) * (NV * 3) + (size_t)slice * VPB * 3;
     for (int e = tid * 2; e < nvalid; e += VPB * 2) {
@@ -409,6 +411,8 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(Mano
 
 #pragma unroll
   for (int sub = 0; sub < HBF / HSUB; ++sub) {
+    // small batches: the group's passes are split over gridDim.z CTAs (block-uniform; the loop stays unrolled)
+    if (gridDim.z > 1 && sub != (int)blockIdx.z) continue;
 #pragma unroll
     for (int hh = 0; hh < HSUB; ++hh) {
       if (USE_VP) {
@@ -931,6 +935,16 @@ static bool use_tc() {
   return g_mano_tc == 1;
 }
 
+// CTAs per (16-hand group, vertex slice) of the skinning kernels: the group's hands are split over two CTAs (shorter serial
+// chain per CTA, twice the CTAs in flight).  Measured fwd+bwd of one side, 1 vs 2: 1024 hands 162 -> 145 us, 2048 221 -> 207,
+// 4096 344 -> 337, 8192 626 -> 614.  HB_MANO_HSPLIT=1 restores one CTA per pair.
+static unsigned skin_hsplit(int B) {
+  (void)B;
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("HB_MANO_HSPLIT"); forced = e ? atoi(e) : 0; }
+  return forced == 1 ? 1u : 2u;
+}
+
 static const size_t kSkinFwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + HBF * XS);
 static const size_t kSkinFwdSmemTc = sizeof(float) * (HBF * AS + HBF * 8 + HBF * XS);
 static const size_t kSkinBwdSmem = sizeof(float) * (FS * HBF + HBF * AS + HBF * 8 + 2 * HSUB * XS + VPB * 3 * HSUB + HSUB * 8 + (VPB / 32) * HSUB * 8);
@@ -962,7 +976,7 @@ extern "C" int hb_mano_head_fwd(const hb_mano* h, const float* pose, int pose_fo
   rc = check_launch("mano_pose_fwd_kernel");
   if (rc) return rc;
   SkinFwdOut o{vertices, v3d_cam, joints3d, j3d_cam, j2d_norm};
-  dim3 grid((unsigned)ws_groups(B), NSLICE);
+  dim3 grid((unsigned)ws_groups(B), NSLICE, skin_hsplit(B));
   if (tc) {
     rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
     if (rc) return rc;
@@ -1005,7 +1019,7 @@ static int mano_head_bwd_impl(const hb_mano* h, const float* pose, int pose_form
     if (rc) return rc;
   }
   SkinBwdIn gi{g_vertices, g_v3d_cam, g_joints3d, g_j3d_cam, g_j2d_norm};
-  dim3 grid((unsigned)ws_groups(B), NSLICE);
+  dim3 grid((unsigned)ws_groups(B), NSLICE, skin_hsplit(B));
   if (tc) {
     if (!reuse) {
       rc = launch_blend_tc(fh, fl, h->c.Bhi, h->c.Blo, h->c.Vt, B, vpo, st);
