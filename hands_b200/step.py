@@ -82,6 +82,10 @@ class GeometryStep:
             self.mano_ws_bytes = self.lib.hb_mano_workspace_bytes(S, 1)
             self.mano_ws = [torch.empty((self.mano_ws_bytes + 3) // 4, **f32) for _ in range(hands_per_sample)]
             self.mano_fwd_valid = [False] * hands_per_sample
+        # second stream for the left hand side of the fused step (HB_STEP_MANO_STREAMS=1: everything on one stream)
+        self.mano_side_stream = None
+        if with_mano and hands_per_sample == 2 and os.environ.get("HB_STEP_MANO_STREAMS", "2") != "1":
+            self.mano_side_stream = torch.cuda.Stream(device=self.dev)
 
     # ---- pieces (each enqueues on the CURRENT torch stream) ------------------------------------
     def _st(self):
@@ -131,10 +135,11 @@ class GeometryStep:
     def run(self):
         """Enqueue one full fwd+bwd step on the current stream.
 
-        One stream on purpose.  Round 1 ran MANO on a second stream "overlapped" with the crop layer; measured, the fused
-        step took exactly the sum of its families (10.84 vs 10.87 ms): every PCL kernel fills the register file (5 x 256 x 48,
-        3 x 256 x 80, 4 x 256 x 62 registers per SM), so no MANO CTA can become resident beside one, whatever the stream
-        priorities -- the second stream only queued.  The MANO share is cut in the kernels instead."""
+        The crop layer and MANO share one stream on purpose.  Round 1 ran MANO on a second stream "overlapped" with the crop
+        layer; measured, the fused step took exactly the sum of its families (10.84 vs 10.87 ms): every PCL kernel fills the
+        register file (5 x 256 x 48, 3 x 256 x 80, 4 x 256 x 62 registers per SM), so no MANO CTA can become resident beside
+        one, whatever the stream priorities -- the second stream only queued.  What does overlap is MANO with itself: the
+        right and the left hand side run on two forked streams (10.31 -> 10.19 ms per 8192-sample step)."""
         with torch.cuda.device(self.dev):   # launches and cudaFuncSetAttribute target self.dev whatever the caller's device
             if self.with_pcl:
                 self.pcl_setup()
@@ -142,10 +147,24 @@ class GeometryStep:
             if self.with_mano:
                 if self.with_pcl:
                     self.gather_pre_rot()
-                for side in range(self.hps):
-                    self.mano_forward(side)
-                for side in range(self.hps):
-                    self.mano_backward(side)
+                if self.hps == 2 and self.mano_side_stream is not None:
+                    # the two hand sides are independent (own constants, inputs, workspace): the left side runs on a forked
+                    # stream, so its latency-bound kernels (pose, the tcgen05 contractions: at most one CTA per SM) share the
+                    # GPU with the right side's skinning kernels; joined before the crop layer's backward.  Inside a capture
+                    # this becomes two parallel branches of the graph.
+                    cur = torch.cuda.current_stream(self.dev)
+                    self.mano_side_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.mano_side_stream):
+                        self.mano_forward(1)
+                        self.mano_backward(1)
+                    self.mano_forward(0)
+                    self.mano_backward(0)
+                    cur.wait_stream(self.mano_side_stream)
+                else:
+                    for side in range(self.hps):
+                        self.mano_forward(side)
+                    for side in range(self.hps):
+                        self.mano_backward(side)
             if self.with_pcl:
                 self.pcl_backward()
 
