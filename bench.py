@@ -282,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
         fused_ms = elapsed / args.steps * 1e3
         overlap = {"fused_ms": fused_ms, "sum_of_families_ms": (t_fwd + t_bwd + t_mf + t_mb) * 1e3,
                    "pcl_alone_ms": (t_fwd + t_bwd) * 1e3, "mano_alone_ms": (t_mf + t_mb) * 1e3,
-                   "note": "one stream: the PCL kernels fill the register file, no MANO CTA can be co-resident (hands_b200/step.py)"}
+                   "note": "PCL and MANO on one stream (the PCL kernels fill the register file, no MANO CTA can be co-resident); the right and left MANO sides run as two forked branches (hands_b200/step.py)"}
         Sk = min(S, 1024)
         ks = step if S == Sk else GeometryStep(Sk, dev, img_res=IMG_RES, seed=7)
         ks.pcl_setup()
@@ -365,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
                    "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
-                   "streams": "single", "cuda_graph": bool(graph_launches),
+                   "streams": "one + a forked branch for the left-hand MANO side" if step.mano_side_stream is not None else "single", "cuda_graph": bool(graph_launches),
                    "pcl_forward": "exact (torch op order)" if os.environ.get("HB_PCL_EXACT", "0") == "1" else "default (reference sample positions, separable resize)",
                    "mano_contractions": "tcgen05 3xTF32" if os.environ.get("HB_MANO_TC", "1") != "0" else "ffma"},
         "clocks": clocks,
