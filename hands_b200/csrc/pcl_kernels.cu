@@ -1129,7 +1129,7 @@ constexpr int PCL_REG = 1536;           // region pixels staged in shared memory
 // g_img is written once per pixel: no float atomics, no memset.
 constexpr int PCL_RECS = 4;            // crop records cached in shared memory per image
 
-template <int C, int RT>
+template <int C, int RT, bool LIST = false>   // LIST: walk the images of a list (fall-back of the scatter form) instead of image blockIdx.y
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img,
                                                                   const int* __restrict__ list) {
@@ -1149,10 +1149,10 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
   const int lx = threadIdx.x & 31, lyb = threadIdx.x >> 5;  // 32 x 8 threads, 4 adjacent rows each
   __shared__ float recs[PCL_RECS * PF];
-  const int n_list = list ? __ldg(list) : (int)gridDim.y;
-  for (int le = blockIdx.y; le < n_list; le += gridDim.y) {
-  const int im = list ? __ldg(list + 1 + le) : img_base + (int)blockIdx.y;
-  __syncthreads();   // the previous image's readers are done with recs
+  const int n_list = LIST ? __ldg(list) : 1;
+  for (int le = LIST ? (int)blockIdx.y : 0; le < n_list; le += LIST ? (int)gridDim.y : 1) {
+  const int im = LIST ? __ldg(list + 1 + le) : img_base + (int)blockIdx.y;
+  if (LIST) __syncthreads();   // the previous image's readers are done with recs
   float acc[4][C];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -1798,6 +1798,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
   const bool scatter = pcl_scatter() && C == 3 && R == 224 && crops_per_img <= PCL_SC_MAXC;
   const size_t smem_sc = sizeof(float) * 3 * PCL_SC_H * (size_t)(R + 2 * PCL_SC_PAD);
   if (scatter) HB_CUDA(cudaFuncSetAttribute(pcl_bwd_scatter_kernel<224>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+  if (scatter) HB_CUDA(cudaFuncSetAttribute(pcl_bwd_img_kernel<C, 224, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PCL_REG * 24 + PCL_CNT_BYTES + PCL_LST_BYTES + 128 * sizeof(float))));
   int* fb_list = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + (size_t)chunk_imgs * pcl_ws_g_bytes_per_img(crops_per_img, R));
   const int tiles = ((R + PCL_TS - 1) / PCL_TS) * ((R + PCL_TS - 1) / PCL_TS);
   const size_t smem_img = (size_t)PCL_REG * 24 + PCL_CNT_BYTES + PCL_LST_BYTES + 128 * sizeof(float);
@@ -1819,7 +1820,7 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
       pcl_fallback_list_kernel<<<1, 1024, 0, st>>>(params, im0, nim, crops_per_img, fb_list);
       pcl_bwd_scatter_kernel<224><<<nim, PCL_SC_THREADS, smem_sc, st>>>(params, ws, im0, crops_per_img, g_img);
       dim3 g3(tiles, nim < 8 ? nim : 8);   // the listed images (usually none) walked by 8 CTA rows
-      img_kernel<<<g3, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, fb_list);
+      pcl_bwd_img_kernel<C, 224, true><<<g3, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, fb_list);
       g_launches += 3;
       rc = check_launch("pcl_bwd_scatter_kernel");
       if (rc) return rc;
