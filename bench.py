@@ -209,6 +209,7 @@ def run_ours(args, rank, world, local_rank):
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "note": "single rank: not bound (the CPU baseline leg uses every core)"}
     S = args.samples
     step = GeometryStep(S, dev, img_res=IMG_RES, seed=rank)
+    streams_desc = "one + a forked branch for the left-hand MANO side" if step.mano_side_stream is not None else "single"
     metrics_vec = torch.zeros(64, device=dev)
 
     graph_launches = 0
@@ -365,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
                    "samples_per_gpu": S, "global_samples": S * world, "hands_per_sample": HANDS_PER_SAMPLE, "img_res": IMG_RES,
                    "bbox_side": "U{56..168}", "grads_on": ["v3d.cam", "j3d.cam", "j2d.norm", "crops"], "parallelism": f"dp{world} (batch sharded, no data-path collective)",
                    "l2": "inputs larger than L2 (%.1f GB working set per GPU), no flush needed" % (step_bytes / 1e9),
-                   "streams": "one + a forked branch for the left-hand MANO side" if step.mano_side_stream is not None else "single", "cuda_graph": bool(graph_launches),
+                   "streams": streams_desc, "cuda_graph": bool(graph_launches),
                    "pcl_forward": "exact (torch op order)" if os.environ.get("HB_PCL_EXACT", "0") == "1" else "default (reference sample positions, separable resize)",
                    "mano_contractions": "tcgen05 3xTF32" if os.environ.get("HB_MANO_TC", "1") != "0" else "ffma"},
         "clocks": clocks,
