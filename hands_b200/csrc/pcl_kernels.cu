@@ -1133,7 +1133,9 @@ constexpr int PCL_REG = 1536;           // region pixels staged in shared memory
 // g_img is written once per pixel: no float atomics, no memset.
 constexpr int PCL_RECS = 4;            // crop records cached in shared memory per image
 
-template <int C, int RT, bool LIST = false>   // LIST: walk the images of a list (fall-back of the scatter form) instead of image blockIdx.y
+// WALK: blockIdx.x is a ROW of tiles and the CTA walks its tiles left to right (the image's records are fetched once per row
+// instead of once per tile, tiles no crop touches cost no launch and no load latency of their own)
+template <int C, int RT, bool LIST = false, int WALK = 0>   // WALK: tile rows per CTA (0: one CTA per tile)   // LIST: walk the images of a list (fall-back of the scatter form) instead of image blockIdx.y
 __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float* __restrict__ params, const float* __restrict__ ws,
                                                                   int img_base, int crops_per_img, int R_arg, float* __restrict__ g_img,
                                                                   const int* __restrict__ list) {
@@ -1150,22 +1152,25 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
   __shared__ int overflow;
   __shared__ int box[4];
   const int tiles_x = (R + PCL_TS - 1) / PCL_TS;
-  const int tx0 = (blockIdx.x % tiles_x) * PCL_TS, ty0 = (blockIdx.x / tiles_x) * PCL_TS;
   const int lx = threadIdx.x & 31, lyb = threadIdx.x >> 5;  // 32 x 8 threads, 4 adjacent rows each
   __shared__ float recs[PCL_RECS * PF];
   const int n_list = LIST ? __ldg(list) : 1;
   for (int le = LIST ? (int)blockIdx.y : 0; le < n_list; le += LIST ? (int)gridDim.y : 1) {
   const int im = LIST ? __ldg(list + 1 + le) : img_base + (int)blockIdx.y;
   if (LIST) __syncthreads();   // the previous image's readers are done with recs
+  // the records of the image's (first PCL_RECS) crops are fetched once, all fields in flight together, instead of a chain
+  // of dependent global loads per crop
+  for (int e = threadIdx.x; e < min(crops_per_img, PCL_RECS) * PF; e += PCL_THREADS) recs[e] = __ldg(params + (size_t)im * crops_per_img * PF + e);
+  __syncthreads();
+  for (int tw = 0; tw < (WALK ? tiles_x * WALK : 1); ++tw) {
+  const int trow = WALK ? (int)blockIdx.x * WALK + tw / tiles_x : (int)(blockIdx.x / tiles_x);
+  if (WALK > 1 && trow * PCL_TS >= R) break;
+  const int tx0 = WALK ? (tw % tiles_x) * PCL_TS : (int)(blockIdx.x % tiles_x) * PCL_TS, ty0 = trow * PCL_TS;
   float acc[4][C];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) acc[r][ch] = 0.f;
-  // the records of the image's (first PCL_RECS) crops are fetched once, all fields in flight together, instead of a chain
-  // of dependent global loads per crop
-  for (int e = threadIdx.x; e < min(crops_per_img, PCL_RECS) * PF; e += PCL_THREADS) recs[e] = __ldg(params + (size_t)im * crops_per_img * PF + e);
-  __syncthreads();
   for (int k = 0; k < crops_per_img; ++k) {
     if (k >= PCL_RECS) {   // more crops per image than cached records: fetch this one into slot 0 (block-uniform)
       __syncthreads();
@@ -1356,6 +1361,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     float* op = g_img + (size_t)im * C * R * R + sy * R + sx;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) __stcs(op + ch * R * R, acc[r][ch]);
+  }
   }
   }
 }
@@ -1829,7 +1835,14 @@ static int launch_bwd(const float* g_out, const float* params, int n_crops, int 
       rc = check_launch("pcl_bwd_scatter_kernel");
       if (rc) return rc;
     } else if (stages & 2) {
-      img_kernel<<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, nullptr);
+      static int walk = -1;   // HB_PCL_IMG_WALK=0: one CTA per tile instead of one per row of tiles
+      if (walk < 0) { const char* e = getenv("HB_PCL_IMG_WALK"); walk = (e && e[0] == '0') ? 0 : 1; }
+      if (walk && R == 224 && crops_per_img <= PCL_RECS) {   // measured per 1024 / 4096 images: one CTA per tile 388 / 1513 us, per tile row 361 / 1352, per two rows 406 / 1456, per image 489 / 1491
+        HB_CUDA(cudaFuncSetAttribute(pcl_bwd_img_kernel<C, 224, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
+        pcl_bwd_img_kernel<C, 224, false, 1><<<dim3((R + PCL_TS - 1) / PCL_TS, nim), PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, nullptr);
+      } else {
+        img_kernel<<<g2, PCL_THREADS, smem_img, st>>>(params, ws, im0, crops_per_img, R, g_img, nullptr);
+      }
       g_launches++;
       rc = check_launch("pcl_bwd_img_kernel");
       if (rc) return rc;
