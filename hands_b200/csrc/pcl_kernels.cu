@@ -1186,44 +1186,37 @@ __global__ void __launch_bounds__(PCL_THREADS, 4) pcl_bwd_img_kernel(const float
     const float* base = ws + __float_as_int(*(rec + 21));
     const float4* G = reinterpret_cast<const float4*>(base);
     __syncthreads();  // previous crop's readers are done with cnt/lst/ent and the region box
-    if (threadIdx.x < 32) {
-      // 1. (warp 0) region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
-      //    sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5); the pre-image
-      //    of that box under the inverse homography is a convex quad, bounded by the box of its four corners
-      float Pi[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Pi[e] = *(rec + 9 + e);
+    // 1. region of the intermediate grid whose samples can land in cells [tx0-1, tx0+31] x [ty0-1, ty0+31]:
+    //    sample positions in [tx0-1, tx0+32) <=> grid-sample pixel coordinates in [tx0-0.5, tx0+32.5); the pre-image
+    //    of that box under the inverse homography is a convex quad, bounded by the box of its four corners.  EVERY warp
+    //    computes it (lanes 0..3 one corner each, then a shuffle reduction): the same values in all warps, no single-warp
+    //    section, and the counters / linspace tables are set up in the same barrier interval.
+    int ri0, ri1, rj0, rj1;
+    {
+      const int ln = threadIdx.x & 31;
       const float sm1 = (float)(s - 1);
-      float ilo = 3.0e38f, ihi = -3.0e38f, jlo = 3.0e38f, jhi = -3.0e38f;
-      bool bad = false;
+      const float gx = (float)tx0 - 0.5f + 33.0f * (float)(ln & 1), gy = (float)ty0 - 0.5f + 33.0f * (float)((ln >> 1) & 1);
+      const float U = rec[9] * gx + rec[10] * gy + rec[11];
+      const float V = rec[12] * gx + rec[13] * gy + rec[14];
+      const float Wd = rec[15] * gx + rec[16] * gy + rec[17];
+      const bool okc = Wd > 1e-12f;
+      const float iw = __frcp_rn(okc ? Wd : 1.0f);
+      const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
+      float ilo = mi, ihi = mi, jlo = mj, jhi = mj;
 #pragma unroll
-      for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-        for (int cx = 0; cx < 2; ++cx) {
-          const float gx = (float)tx0 - 0.5f + 33.0f * cx, gy = (float)ty0 - 0.5f + 33.0f * cy;
-          const float U = Pi[0] * gx + Pi[1] * gy + Pi[2];
-          const float V = Pi[3] * gx + Pi[4] * gy + Pi[5];
-          const float Wd = Pi[6] * gx + Pi[7] * gy + Pi[8];
-          if (Wd > 1e-12f) {
-            const float iw = __frcp_rn(Wd);
-            const float mi = fminf(fmaxf(U * iw * sm1, -8.0f), sm1 + 8.0f), mj = fminf(fmaxf(V * iw * sm1, -8.0f), sm1 + 8.0f);
-            ilo = fminf(ilo, mi); ihi = fmaxf(ihi, mi); jlo = fminf(jlo, mj); jhi = fmaxf(jhi, mj);
-          } else bad = true;
-        }
-      if (threadIdx.x == 0) {
-        if (bad) { box[0] = 0; box[1] = s - 1; box[2] = 0; box[3] = s - 1; }
-        else {
-          box[0] = max(0, (int)floorf(ilo - 0.25f)); box[1] = min(s - 1, (int)ceilf(ihi + 0.25f));
-          box[2] = max(0, (int)floorf(jlo - 0.25f)); box[3] = min(s - 1, (int)ceilf(jhi + 0.25f));
-        }
-        overflow = 0;
+      for (int m = 1; m < 4; m <<= 1) {
+        ilo = fminf(ilo, __shfl_xor_sync(0xffffffffu, ilo, m)); ihi = fmaxf(ihi, __shfl_xor_sync(0xffffffffu, ihi, m));
+        jlo = fminf(jlo, __shfl_xor_sync(0xffffffffu, jlo, m)); jhi = fmaxf(jhi, __shfl_xor_sync(0xffffffffu, jhi, m));
       }
-    } else {
-      for (int idx = threadIdx.x - 32; idx < (PCL_CELLS * PCL_CELLS + 3) / 4; idx += PCL_THREADS - 32) reinterpret_cast<int4*>(cnt)[idx] = make_int4(0, 0, 0, 0);
+      const bool bad = (__ballot_sync(0xffffffffu, !okc) & 0xfu) != 0;
+      ilo = __shfl_sync(0xffffffffu, ilo, 0); ihi = __shfl_sync(0xffffffffu, ihi, 0);
+      jlo = __shfl_sync(0xffffffffu, jlo, 0); jhi = __shfl_sync(0xffffffffu, jhi, 0);
+      ri0 = bad ? 0 : max(0, (int)floorf(ilo - 0.25f)); ri1 = bad ? s - 1 : min(s - 1, (int)ceilf(ihi + 0.25f));
+      rj0 = bad ? 0 : max(0, (int)floorf(jlo - 0.25f)); rj1 = bad ? s - 1 : min(s - 1, (int)ceilf(jhi + 0.25f));
     }
-    __syncthreads();
-    const int ri0 = box[0], ri1 = box[1], rj0 = box[2], rj1 = box[3];
-    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform)
+    if (ri0 > ri1 || rj0 > rj1) continue;  // this crop does not touch the tile (block-uniform: every warp computed the same box)
+    for (int idx = threadIdx.x; idx < (PCL_CELLS * PCL_CELLS + 3) / 4; idx += PCL_THREADS) reinterpret_cast<int4*>(cnt)[idx] = make_int4(0, 0, 0, 0);
+    if (threadIdx.x == 0) overflow = 0;
     const int rw = ri1 - ri0 + 1, rh = rj1 - rj0 + 1;
     const Crop c = load_crop_any(rec);
     float P[9];
@@ -1520,10 +1513,8 @@ __global__ void __launch_bounds__(PCL_SC_THREADS, 2) pcl_bwd_scatter_kernel(cons
               const int fx = (int)fxf, fy = (int)fyf;
               key[h] = ok[h] ? ((fy + 1) << 10) + fx + 1 : -5;
               defer[h] = lane == 31 && i < sm1;   // the next strip's lane 0 handles this sample's right column
-              // (lanes that own nothing point at pad columns nobody reads: the left-column update below needs no branch)
-              const bool own = ok[h] && lane > 0;
-              at[h] = win + (own || ok[h] ? (fy & HM) * W + fx + PCL_SC_PAD : lane & 3);
-              ab[h] = win + (own || ok[h] ? ((fy + 1) & HM) * W + fx + PCL_SC_PAD : lane & 3);
+              at[h] = win + ((fy & HM) * W + fx + PCL_SC_PAD);
+              ab[h] = win + (((fy + 1) & HM) * W + fx + PCL_SC_PAD);
               const float4 g = gq[qp + h];
               gv[h][0] = g.x; gv[h][1] = g.y; gv[h][2] = g.z;
             }
@@ -1547,15 +1538,11 @@ __global__ void __launch_bounds__(PCL_SC_THREADS, 2) pcl_bwd_scatter_kernel(cons
                 const float nwx = fwd_in[h] ? n_ax : 0.0f;
                 const float bx = 1.0f - ax[h], by = 1.0f - ay[h];
                 const float wlt = bx * by, wlb = bx * ay[h], nt = nwx * (1.0f - n_ay), nbm = nwx * n_ay;
-                {
-                  // lane 0 of a later strip is a provider (its sample's left column was the previous strip's), a lane that is
-                  // not ok points at a pad column
-                  float* pt = (ok[h] && lane == 0) ? win + (lane & 3) : at[h];
-                  float* pb = (ok[h] && lane == 0) ? win + (lane & 3) : ab[h];
+                if (ok[h] && lane > 0) {   // lane 0 of a later strip is a provider: its sample's left column was the previous strip's
 #pragma unroll
                   for (int ch = 0; ch < 3; ++ch) {
-                    pt[ch * PLANE] = fmaf(wlt, gv[h][ch], fmaf(nt, ng[ch], pt[ch * PLANE]));
-                    pb[ch * PLANE] = fmaf(wlb, gv[h][ch], fmaf(nbm, ng[ch], pb[ch * PLANE]));
+                    at[h][ch * PLANE] = fmaf(wlt, gv[h][ch], fmaf(nt, ng[ch], at[h][ch * PLANE]));
+                    ab[h][ch * PLANE] = fmaf(wlb, gv[h][ch], fmaf(nbm, ng[ch], ab[h][ch * PLANE]));
                   }
                 }
                 const bool sent = lane < 31 && ((m_fwd >> (lane + 1)) & 1u);   // my right column went to lane + 1
@@ -1664,7 +1651,7 @@ __global__ void __launch_bounds__(1024) pcl_fallback_list_kernel(const float* __
 
 using namespace hb;
 
-static int g_pcl_scatter = -1;   // -1: not decided yet (env HB_PCL_SCATTER, default 0: measured 527 vs 399 us per 1024 images)
+static int g_pcl_scatter = -1;   // -1: not decided yet (env HB_PCL_SCATTER, default 0: measured ~530 vs 361 us per 1024 images)
 static int pcl_scatter() {
   if (g_pcl_scatter < 0) { const char* e = getenv("HB_PCL_SCATTER"); g_pcl_scatter = (e && e[0] == '1') ? 1 : 0; }
   return g_pcl_scatter;
