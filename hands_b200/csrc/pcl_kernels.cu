@@ -970,7 +970,7 @@ __global__ void __launch_bounds__(PCL_MT) pcl_bwd_mid_kernel(const float* __rest
 //                    control are paid once per 4*C FMAs; it then writes the gradient.
 constexpr int PCL_MG = 4;               // row groups (two warps each)
 constexpr int PCL_M4T = 64 * PCL_MG;     // threads per CTA
-constexpr int PCL_MU = 2;               // output rows in flight per thread in the vertical pass
+constexpr int PCL_MU = 2;               // output rows in flight per thread in the vertical pass (3: 427 vs 377 us, spills)
 constexpr int PCL_MB = 2;               // bands per CTA (measured per 1024 / 4096 images: 1 -> 380.9 / 1473.5 us, 2 -> 376.8 / 1442.5, 4 -> 388.8 / 1445.7)
 
 template <int C, int RT>
