@@ -1,5 +1,12 @@
-import os, sys, torch
-sys.path.insert(0, '/root/repo')
+"""Crop-layer backward under compute-sanitizer (memcheck / racecheck): gather form (tile-row CTAs), scatter form and its
+fall-back list, two and three crops per image, a whole-image box and a short focal length.
+    compute-sanitizer --tool racecheck python scripts/sanitize_pcl_bwd.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hands_b200 import _lib
 from hands_b200.pcl import perspective_crop
 from hands_b200.synthetic import synthetic_pcl_inputs
