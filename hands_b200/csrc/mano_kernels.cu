@@ -291,7 +291,9 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 3) mano_skin_fwd_kernel(Mano
     const float4* srcA = reinterpret_cast<const float4*>(ws + ws_A(B) + (size_t)g * HBF * AS);
     const float4* srcO = reinterpret_cast<const float4*>(ws + ws_OFF(B) + (size_t)g * HBF * 8);
     if (!USE_VP) for (int idx = tid; idx < FS * HBF / 4; idx += VPB) reinterpret_cast<float4*>(Fs)[idx] = srcF[idx];
-    for (int idx = tid; idx < HBF * AS / 4; idx += VPB) reinterpret_cast<float4*>(As)[idx] = srcA[idx];
+    // (only the transforms of this CTA's share of the group's hands)
+    const int a0 = (int)blockIdx.z * (HBF / (int)gridDim.z) * AS / 4, a1 = a0 + (HBF / (int)gridDim.z) * AS / 4;
+    for (int idx = a0 + tid; idx < a1; idx += VPB) reinterpret_cast<float4*>(As)[idx] = srcA[idx];
     for (int idx = tid; idx < HBF * 8 / 4; idx += VPB) reinterpret_cast<float4*>(Os)[idx] = srcO[idx];
   }
   __syncthreads();
@@ -396,7 +398,9 @@ __global__ void __launch_bounds__(VPB, USE_VP ? 5 : 2) mano_skin_bwd_kernel(Mano
     const float4* srcA = reinterpret_cast<const float4*>(ws + ws_A(B) + (size_t)g * HBF * AS);
     const float4* srcO = reinterpret_cast<const float4*>(ws + ws_OFF(B) + (size_t)g * HBF * 8);
     if (!USE_VP) for (int idx = tid; idx < FS * HBF / 4; idx += VPB) reinterpret_cast<float4*>(Fs)[idx] = srcF[idx];
-    for (int idx = tid; idx < HBF * AS / 4; idx += VPB) reinterpret_cast<float4*>(As)[idx] = srcA[idx];
+    // (only the transforms of this CTA's share of the group's hands)
+    const int a0 = gridDim.z > 1 ? (int)blockIdx.z * HSUB * AS / 4 : 0, a1 = gridDim.z > 1 ? a0 + HSUB * AS / 4 : HBF * AS / 4;
+    for (int idx = a0 + tid; idx < a1; idx += VPB) reinterpret_cast<float4*>(As)[idx] = srcA[idx];
     for (int idx = tid; idx < HBF * 8 / 4; idx += VPB) reinterpret_cast<float4*>(Os)[idx] = srcO[idx];
   }
   __syncthreads();
