@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
     float* stile = reinterpret_cast<float*>(mid4 + cap);   // source tile [C][rows][cols] fp32, cols a multiple of 4
     const int tile_bytes = smem_bytes - cap * 16;
     // warp 0: tile record of the band starting at output row y0 (+ the TMA bulk copies for an fp32 image)
-    auto issue_tile = [&](int y0, int slot) {
+    auto issue_tile = [&](int y0, int slot, int jdone) {   // jdone: last intermediate row the previous band left in the ring (-1: none)
       // The band's sample positions are the image of a rectangle of the intermediate grid under a homography: a convex
       // quad whose corner box (+ the bilinear margin) bounds every tap.  The tile spans that box in UNCLAMPED image
       // coordinates, at most [-1, R]: the parts outside the image are the reference's zero padding, so the gather needs
@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
       float l0, l1;
       resize_coef(c, y0, R, jlo, t1, l0, l1);
       resize_coef(c, y1, R, t0, jhi, l0, l1);
+      jlo = max(jlo, jdone + 1);   // the band's rows up to jdone are already in the ring: the tile covers the new rows only
       float cx = 0.f, cy = 0.f;
       if (lane < 4) sample_pos_uv(c, lin01(c, (lane & 1) ? ihi : ilo), lin01(c, (lane >> 1) ? jhi : jlo), Rf, rcpR, cx, cy);
       float xmn = lane < 4 ? cx : 3.0e38f, xmx = lane < 4 ? cx : -3.0e38f, ymn = lane < 4 ? cy : 3.0e38f, ymx = lane < 4 ? cy : -3.0e38f;
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
       xmn = __shfl_sync(0xffffffffu, xmn, 0); xmx = __shfl_sync(0xffffffffu, xmx, 0);
       ymn = __shfl_sync(0xffffffffu, ymn, 0); ymx = __shfl_sync(0xffffffffu, ymx, 0);
       int use = 0, bx0 = 0, by0 = 0, ncols = 0, nr = 0;
-      if (tma_ok && xmn == xmn && xmx == xmx && ymn == ymn && ymx == ymx && xmx > -2.0f && ymx > -2.0f && xmn < Rf + 1.0f && ymn < Rf + 1.0f) {
+      if (tma_ok && jlo <= jhi && xmn == xmn && xmx == xmx && ymn == ymn && ymx == ymx && xmx > -2.0f && ymx > -2.0f && xmn < Rf + 1.0f && ymn < Rf + 1.0f) {
         const int xl = max(-1, (int)floorf(fmaxf(xmn, -4.0f)) - 1), xh = min(R, (int)floorf(fminf(xmx, Rf + 4.0f)) + 2);
         const int yl = max(-1, (int)floorf(fmaxf(ymn, -4.0f)) - 1), yh = min(R, (int)floorf(fminf(ymx, Rf + 4.0f)) + 2);
         bx0 = xl & ~3;                      // two's complement: -1 -> -4
@@ -548,8 +549,12 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
     };
     if (tid == 0) { mbar_init(&src_bar, 1); mbar_fence_init(); }
     __syncwarp();
-    if (tid < 32) issue_tile(Y0, 0);
+    if (tid < 32) issue_tile(Y0, 0, -1);
     int nuse = 0, slot = 0;
+    // The band buffer is a ring of RG intermediate rows: consecutive bands share their last 2-3 rows (the resize's halo), which
+    // stay where they are -- a band gathers only the rows above the previous band's last one, and its tile covers only those.
+    const int RG = band_rows(rows_sub);
+    int jdone = -1, ring_lo = 0, jlo_prev = 0;   // ring_lo: ring slot of row jlo_prev
     const int q256 = small_div(PCL_THREADS, ncol), r256 = PCL_THREADS - q256 * ncol;   // idx += 256  <=>  (row += q256, col += r256) with one carry
     for (int y0 = Y0; y0 <= Y1; y0 += rows_sub, slot ^= 1) {
       const int y1 = min(y0 + rows_sub - 1, Y1);
@@ -557,15 +562,25 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
       float l0, l1;
       resize_coef(c, y0, R, jlo, t1, l0, l1);
       resize_coef(c, y1, R, t0, jhi, l0, l1);
-      const int nrows = jhi - jlo + 1;
+      // ring slot of row jlo (rows advance by less than RG per band)
+      if (jdone >= 0) { ring_lo += jlo - jlo_prev; if (ring_lo >= RG) ring_lo -= RG; }
+      jlo_prev = jlo;
+      const int jnew = max(jlo, jdone + 1);            // first row this band has to gather
+      const int nrows = jhi - jnew + 1;                // new rows (>= 0)
       const int n = nrows * ncol;                      // <= cap
-      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this band (band-row byte offsets)
+      int snew = ring_lo + (jnew - jlo);               // ring slot of row jnew
+      if (snew >= RG) snew -= RG;
+      if (tid >= 32 && tid - 32 < y1 - y0 + 1) {   // per-row resize coefficients of this band (ring-row byte offsets)
         int a0, a1;
         float ly0, ly1;
         resize_coef(c, y0 + tid - 32, R, a0, a1, ly0, ly1);
-        rowrec[tid - 32] = make_float4(ly0, ly1, __int_as_float((a0 - jlo) * ncol * 16), __int_as_float((a1 - jlo) * ncol * 16));
+        int s0 = ring_lo + (a0 - jlo), s1 = ring_lo + (a1 - jlo);
+        if (s0 >= RG) s0 -= RG;
+        if (s1 >= RG) s1 -= RG;
+        rowrec[tid - 32] = make_float4(ly0, ly1, __int_as_float(s0 * ncol * 16), __int_as_float(s1 * ncol * 16));
       }
-      if (RT && tid >= 64 && tid - 64 < nrows && tid - 64 < PCL_TV) tv[tid - 64] = lin01(c, jlo + tid - 64);
+      if (RT && tid >= 64 && tid - 64 < nrows && tid - 64 < PCL_TV) tv[tid - 64] = lin01(c, jnew + tid - 64);
+      jdone = jhi;
       __syncthreads();   // tile record, row table, linspace tables, barrier init (and the LUT) are visible
       const int rx0 = reg[slot][0], ry0 = reg[slot][1], rnc = reg[slot][2], rnr = reg[slot][3];
       const bool tiled = reg[slot][4] != 0;
@@ -607,7 +622,7 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
         for (int idx = tid; idx < n; idx += PCL_THREADS) {
           float ix, iy;
           if (RT) sample_pos_uv(c, tu[i], tv[min(jr, PCL_TV - 1)], Rf, rcpR, ix, iy);
-          else sample_pos_uv(c, lin01(c, ilo + i), lin01(c, jlo + jr), Rf, rcpR, ix, iy);
+          else sample_pos_uv(c, lin01(c, ilo + i), lin01(c, jnew + jr), Rf, rcpR, ix, iy);
           float v[4];
           // both taps of each axis inside the tile?  (float compares: a NaN position fails them and takes the fallback)
           if (tiled && ix >= xlo && ix < xhi && iy >= ylo && iy < yhi) {
@@ -632,14 +647,18 @@ __global__ void __launch_bounds__(PCL_THREADS, 5) pcl_fwd_fast_kernel(const SrcT
           } else {   // tile not staged (does not fit / unaligned image), position outside the image, or a tap outside the tile
             gather_global<C, SrcT>(src, lut, R, plane, ix, iy, v);
           }
-          mid4[idx] = make_float4(v[0], v[1], v[2], v[3]);
+          {
+            int sl = snew + jr;   // ring slot of this row
+            if (sl >= RG) sl -= RG;
+            mid4[sl * ncol + i] = make_float4(v[0], v[1], v[2], v[3]);
+          }
           i += r256; jr += q256;
           if (i >= ncol) { i -= ncol; ++jr; }
         }
       }
       __syncthreads();   // the band is complete; the tile is free
       // the next band's tile flies while this band is resized: warp 0 is the producer, warps 1..7 resize
-      if (tid < 32 && y0 + rows_sub <= Y1) issue_tile(y0 + rows_sub, slot ^ 1);
+      if (tid < 32 && y0 + rows_sub <= Y1) issue_tile(y0 + rows_sub, slot ^ 1, jhi);
       // separable resize: a thread owns two adjacent output columns of one group of the band's rows; the two live
       // intermediate rows, interpolated horizontally, stay in registers while consecutive output rows share them
       if (tid >= 32) {
