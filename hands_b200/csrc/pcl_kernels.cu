@@ -15,7 +15,9 @@
 //                      intermediate grid that can reach a 32x32 source tile is staged with cp.async, its sample
 //                      positions recomputed and binned into per-cell lists; each source pixel collects exactly its
 //                      contributors in a fixed order, so g_img is written once -- no float atomics, no memset,
-//                      bit-reproducible.
+//                      bit-reproducible.  One CTA per ROW of tiles of an image.
+//   pcl_bwd_scatter  : the same operator as an atomics-free scatter into a rolling shared-memory window of source rows
+//                      (opt-in, HB_PCL_SCATTER=1: measured slower than the gather form; kept with its tests).
 // The fp32 operation order (which products are fused) follows torch's CPU kernels exactly; it was pinned
 // by bit-comparing a numpy emulation against torch 2.11 single-threaded ("PCL exactness").
 #include <climits>
@@ -1143,7 +1145,8 @@ constexpr int PCL_CNT_BYTES = (PCL_CELLS * PCL_CELLS * 4 + 15) & ~15;           
 constexpr int PCL_LST_BYTES = (PCL_CELLS * PCL_CELLS * 2 * PCL_K + 15) & ~15;
 constexpr int PCL_REG = 1536;           // region pixels staged in shared memory per (tile, crop) (39 x 39; 4 CTAs/SM)
 
-// Transposed grid_sample, gather form.  One CTA per (image, 32x32 source tile); for each crop of the image:
+// Transposed grid_sample, gather form.  One CTA per (image, 32x32 source tile) -- or per row of such tiles (WALK) --; for each
+// tile and each crop of the image:
 //   1. the tile's pre-image under the inverse homography bounds a region of the intermediate grid;
 //   2. every intermediate pixel of the region is binned by floor(sample position) into per-cell lists in
 //      shared memory (integer atomics claim the slots);
