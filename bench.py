@@ -214,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
 
     graph_launches = 0
     if not args.no_graph:
-        graph_launches = step.capture()       # the 33 launches of a step replayed from one CUDA graph
+        graph_launches = step.capture()       # the launches of a step replayed from one CUDA graph
 
     def one_step():
         if graph_launches:

@@ -170,7 +170,7 @@ class GeometryStep:
 
     # ---- the same step as one CUDA graph -------------------------------------------------------------
     def capture(self):
-        """Capture one `run()` (33 launches: 19 PCL, 12 MANO, 2 strided copies) into a CUDA graph.  Every buffer is
+        """Capture one `run()` (19 library launches at the recommended workspace size: 7 PCL, 12 MANO; plus 2 strided copies) into a CUDA graph.  Every buffer is
         pre-allocated and every argument is a fixed device pointer, so the step replays verbatim; `replay()` then costs one
         host call and removes the launch gaps between the kernels.  Returns the number of library launches per replay."""
         side = torch.cuda.Stream(device=self.dev)
